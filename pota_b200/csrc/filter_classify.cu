@@ -1,0 +1,121 @@
+// filter_classify.cu — K2a: per-source-sample front half of filter_pixel (compiled with -fmad=false:
+// the splat COUNT of a sample is an integer decision taken from float/double expressions, so they
+// are evaluated operation by operation exactly as the reference's host code does).
+//
+// Reference: /root/reference/src/lentil_filter.cpp:105-246 — read the sample, decide `redistribute`,
+// derive the sample count from CoC^2 x luminance, gather the AOV values, and for samples that are not
+// redistributed do filter_and_add_to_buffer_new (lentil.h:938-955) right here.  Redistributed samples
+// are appended to a work list consumed by the splat kernel (filter_kernels.cu).
+#include "filter_common.cuh"
+
+namespace lb {
+
+// Camera::get_coc_thinlens, lentil.h:674-692 (float arithmetic, as there)
+__device__ float get_coc_thinlens(const FilterConsts &fc, float z) {
+  const float fl = fc.focal_length;
+  const float image_dist_samplepos = (-fl * z) / (-fl + z);
+  const float image_dist_focusdist = (-fl * -fc.coc_focus_distance) / (-fl + -fc.coc_focus_distance);
+  return fabsf((fc.coc_aperture_radius * (image_dist_samplepos - image_dist_focusdist)) / image_dist_samplepos);
+}
+
+// Camera::additional_luminance_soft_trans, lentil.h:1128-1138
+__device__ float additional_luminance_soft_trans(const FilterConsts &fc, float lum) {
+  const double lo = fc.bidir_add_energy_minimum_luminance;
+  if ((double)lum > lo && (double)lum < lo + (double)fc.bidir_add_energy_transition) {
+    const float perc = (float)(((double)lum - lo) / (double)fc.bidir_add_energy_transition);
+    return fc.bidir_add_energy * perc;
+  } else if ((double)lum > lo + (double)fc.bidir_add_energy_transition) {
+    return fc.bidir_add_energy;
+  }
+  return 0.0f;
+}
+
+__global__ void __launch_bounds__(256)
+k_filter_classify(const __grid_constant__ FilterConsts fc, const __grid_constant__ AovSet aovs, const __grid_constant__ SampleIO s,
+                  WorkItem *__restrict__ work, FilterCounters *__restrict__ counters, uint64_t sample_base) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = i < s.n;
+  bool redistribute = active;
+  int samples = 0;
+  float add_energy = 0.f;
+  float csp[3] = {0.f, 0.f, 0.f};
+  if (active) {
+    float4 sample = __ldg(s.rgba + i);
+    const float4 pz = __ldg(s.pos_cs + i);
+    csp[0] = pz.x; csp[1] = pz.y; csp[2] = pz.z;
+    const float depth = pz.w;
+    // lentil_filter.cpp:119-133
+    const bool small = fabsf(csp[0]) < 1.0e-4f && fabsf(csp[1]) < 1.0e-4f && fabsf(csp[2]) < 1.0e-4f;
+    if ((depth == 1.0e30f || small) && fc.enable_skydome) {
+      float4 rd = s.raydir ? __ldg(s.raydir + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (rd.x == 0.f && rd.y == 0.f && rd.z == 0.f) redistribute = false;
+      else { csp[0] = rd.x * 99999999.0f; csp[1] = rd.y * 99999999.0f; csp[2] = rd.z * 99999999.0f; }
+    }
+    if ((depth == 1.0e30f || small) && !fc.enable_skydome) redistribute = false;
+    const uint32_t flags = s.flags ? __ldg(s.flags + i) : 0u;
+    if (flags & 1u) redistribute = false;  // volume_in_sample (:135-137)
+    csp[0] *= fc.unit_mult; csp[1] *= fc.unit_mult; csp[2] *= fc.unit_mult;  // :143-148
+    if (s.transmission) {  // :152-159
+      const float4 t = __ldg(s.transmission + i);
+      const bool transmitted = fc.enable_bidir_transmission ? false : (fmaxf(t.x, fmaxf(t.y, t.z)) > 0.0f);
+      if (transmitted) { sample.x -= t.x; sample.y -= t.y; sample.z -= t.z; redistribute = false; }
+    }
+    const float lum = (float)((double)(sample.x + sample.y + sample.z) / 3.0);  // :161
+    if (flags & 2u) redistribute = false;  // lentil_bidir_ignore (:162-164)
+    if (fc.bidir_add_energy > 0.0f) add_energy = additional_luminance_soft_trans(fc, lum);
+    // :177-179
+    const float luminance_mult = (float)fmax(0.0, sqrt((double)fminf(lum, 20.0f)) * (double)fc.bidir_sample_mult);
+    const float coc = get_coc_thinlens(fc, csp[2]);
+    const float cy = coc * (float)(unsigned)fc.yres;
+    const float coc_squared_pixels = (float)(((double)cy * (double)cy) * ((double)luminance_mult * (double)luminance_mult) * 0.00001);
+    if (coc < 0.4f) redistribute = false;  // :183-187
+    samples = (int)ceilf(coc_squared_pixels * s.inv_density);  // :197
+    float sf = (float)samples;                                  // clamp(float,4,2000), global.h:8-12
+    if (sf < 4.f) sf = 4.f;
+    if (sf > 2000.f) sf = 2000.f;
+    samples = (int)sf;
+    const float debug_val = (float)(samples * (redistribute ? 1 : 0));  // lentil_debug value, taken at :209-211
+    if ((double)fabsf(csp[2]) < fc.lens_length_tenth) redistribute = false;  // :240
+    if (fc.camera_type != 1) redistribute = false;  // only the PolynomialOptics branch is built
+    const int px = __ldg(s.px + i), py = __ldg(s.py + i);
+    if (!redistribute) {
+      // filter_and_add_to_buffer_new (lentil.h:938-955): every AOV, own pixel, weight inv_density
+      const unsigned pixel = (unsigned)fc.xres * (unsigned)py + (unsigned)px;
+      const float white[3] = {1.f, 1.f, 1.f};
+      for (int a = 0; a < fc.n_aov; ++a) {
+        const float4 v = aov_value(aovs, s, a, i, debug_val);
+        add_to_buffer(aovs, a, pixel, v, 0.0f, depth, s.inv_density, white, sample_base + i);
+      }
+    }
+    if (aovs.debug_samples) aovs.debug_samples[i] = (uint16_t)debug_val;
+  }
+  // append redistributed samples to the work list, one atomic per warp
+  const unsigned mask = __ballot_sync(0xffffffffu, redistribute);
+  const int lane = threadIdx.x & 31;
+  unsigned base = 0;
+  if (lane == 0 && mask) base = atomicAdd(&counters->work_count, (unsigned)__popc(mask));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (redistribute) {
+    WorkItem w;
+    w.sample = (uint32_t)i;
+    w.n_samples = (uint32_t)samples;
+    w.add_energy = add_energy;
+    w.csp[0] = csp[0]; w.csp[1] = csp[1]; w.csp[2] = csp[2];
+    work[base + __popc(mask & ((1u << lane) - 1u))] = w;
+  }
+  const unsigned amask = __ballot_sync(0xffffffffu, active);
+  if (lane == 0 && amask) {
+    atomicAdd(&counters->samples, (unsigned long long)__popc(amask));
+    atomicAdd(&counters->redistributed, (unsigned long long)__popc(mask));
+    atomicAdd(&counters->passthrough, (unsigned long long)__popc(amask & ~mask));
+  }
+}
+
+cudaError_t launch_filter_classify(const FilterConsts &fc, const AovSet &aovs, const SampleIO &s, WorkItem *work,
+                                   FilterCounters *counters, uint64_t sample_base, cudaStream_t stream) {
+  if (s.n == 0) return cudaSuccess;
+  k_filter_classify<<<(unsigned)((s.n + 255) / 256), 256, 0, stream>>>(fc, aovs, s, work, counters, sample_base);
+  return cudaGetLastError();
+}
+
+}  // namespace lb

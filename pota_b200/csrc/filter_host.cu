@@ -1,0 +1,439 @@
+// filter_host.cu — host side of the filter / imager / multi-GPU entry points of the C ABI.
+//
+// Owns the device-resident replacements of Camera::aovs[i].buffer, filter_weight_buffer, zbuffer and
+// zbuffer_debug (/root/reference/src/lentil.h:100-103, 1096-1117; aov_data.h:114-164).
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>  // types only: the library is resolved at run time (dlopen), see load_nccl()
+
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "../../include/lentil_b200.h"
+#include "lentil_internal.h"
+
+namespace lb {
+int cam_device(lb_camera *c);
+int cam_num_sms(lb_camera *c);
+const lb_camera_params &cam_params(lb_camera *c);
+const lb_camera_state &cam_state(lb_camera *c);
+const LensTable &cam_lens(lb_camera *c);
+int cam_lens_kernel(lb_camera *c);
+const CamConsts<float> &cam_consts(lb_camera *c);
+struct FilterStateTag;
+std::mutex &cam_mutex(lb_camera *c);
+int lb_fail(int code, const char *msg);
+}  // namespace lb
+using namespace lb;
+
+struct FilterState {
+  lb_frame_desc frame{};
+  int n_aov = 0;
+  lb_aov_desc aovs[kMaxAov]{};
+  size_t npx = 0;
+  float *block = nullptr;  // [n_aov][npx] float4 planes, then [npx] weight: one contiguous reduction unit
+  size_t block_floats = 0;
+  unsigned long long *zkey = nullptr, *zkey_debug = nullptr;
+  bool has_closest = false, has_debug_closest = false;
+  WorkItem *work = nullptr;
+  size_t work_cap = 0;
+  uint16_t *debug_samples = nullptr;
+  FilterCounters *d_counters = nullptr;
+  uint64_t sample_base = 0;
+  // host-path staging
+  char *stage = nullptr;
+  size_t stage_bytes = 0;
+  cudaStream_t stream = nullptr;
+  // NCCL
+  ncclComm_t comm = nullptr;
+  int world = 1, rank = 0;
+};
+namespace lb { FilterState *&cam_filter(lb_camera *c); }
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev); else prev = -1;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+#define CUF(call)                                                                         \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess) return lb_fail(LB_ERR_CUDA, cudaGetErrorString(e_));           \
+  } while (0)
+
+// ---- NCCL through dlopen: the process' already-loaded libnccl.so.2 (e.g. torch's) is reused ----
+struct NcclApi {
+  void *h = nullptr;
+  decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+  decltype(&ncclCommInitRank) CommInitRank = nullptr;
+  decltype(&ncclCommDestroy) CommDestroy = nullptr;
+  decltype(&ncclAllReduce) AllReduce = nullptr;
+  decltype(&ncclReduce) Reduce = nullptr;
+  decltype(&ncclGroupStart) GroupStart = nullptr;
+  decltype(&ncclGroupEnd) GroupEnd = nullptr;
+  decltype(&ncclGetErrorString) GetErrorString = nullptr;
+};
+NcclApi *load_nccl() {
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    const char *names[] = {getenv("LB_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) {
+      if (!n) continue;
+      api.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (api.h) break;
+    }
+    if (!api.h) return;
+#define SYM(f) api.f = (decltype(api.f))dlsym(api.h, "nccl" #f)
+    SYM(GetUniqueId); SYM(CommInitRank); SYM(CommDestroy); SYM(AllReduce); SYM(Reduce); SYM(GroupStart); SYM(GroupEnd); SYM(GetErrorString);
+#undef SYM
+  });
+  return (api.h && api.GetUniqueId && api.CommInitRank && api.AllReduce && api.Reduce) ? &api : nullptr;
+}
+
+void fill_consts(lb_camera *c, const FilterState *f, FilterConsts &fc) {
+  const lb_camera_params &p = cam_params(c);
+  const lb_camera_state &s = cam_state(c);
+  fc.xres = f->frame.xres; fc.yres = f->frame.yres;
+  fc.xres_full = f->frame.xres_without_region; fc.yres_full = f->frame.yres_without_region;
+  fc.region_min_x = f->frame.region_min_x; fc.region_min_y = f->frame.region_min_y;
+  fc.n_aov = f->n_aov;
+  fc.bidir_sample_mult = p.bidir_sample_mult;
+  fc.camera_type = p.camera_type;
+  fc.enable_skydome = p.enable_skydome != 0;
+  fc.enable_bidir_transmission = p.enable_bidir_transmission != 0;
+  const float um[4] = {(float)0.1, (float)1.0, (float)10.0, (float)100.0};
+  fc.unit_mult = um[std::min(std::max(p.units, 0), 3)];
+  fc.focal_length = p.focal_length_lentil < (float)0.01 ? (float)0.01 : p.focal_length_lentil;
+  // get_coc_thinlens prologue (lentil.h:676-687)
+  float fd = (float)s.focus_distance, ar = (float)s.aperture_radius;
+  if (p.camera_type == LB_CAMERA_POLYNOMIAL_OPTICS) fd = (float)((double)fd / 10.0);
+  else ar = (float)((double)ar * 10.0);
+  fc.coc_focus_distance = fd;
+  fc.coc_aperture_radius = ar;
+  fc.lens_length_tenth = s.lens_length * 0.1;
+  fc.bidir_add_energy = p.bidir_add_energy;
+  fc.bidir_add_energy_transition = p.bidir_add_energy_transition;
+  fc.bidir_add_energy_minimum_luminance = p.bidir_add_energy_minimum_luminance;
+  fc.abb_chromatic = p.abb_chromatic;
+  fc.sensor_half = (double)p.sensor_width * 0.5;
+  fc.aspect_full = (double)f->frame.xres_without_region / (double)f->frame.yres_without_region;
+}
+
+void fill_aovs(const FilterState *f, AovSet &A, const float *const *values) {
+  memset(&A, 0, sizeof A);
+  for (int a = 0; a < f->n_aov; ++a) {
+    A.buffer[a] = (float4 *)(f->block + (size_t)a * f->npx * 4);
+    A.values[a] = values ? (const float4 *)values[a] : nullptr;
+    A.filter[a] = f->aovs[a].filter;
+    A.role[a] = f->aovs[a].role;
+  }
+  A.weight = f->block + (size_t)f->n_aov * f->npx * 4;
+  A.zkey = f->zkey;
+  A.zkey_debug = f->zkey_debug;
+  A.debug_samples = f->has_debug_closest ? f->debug_samples : nullptr;
+}
+
+int ensure_batch_capacity(FilterState *f, size_t n) {
+  if (f->work_cap >= n) return LB_OK;
+  cudaFree(f->work); cudaFree(f->debug_samples);
+  f->work = nullptr; f->debug_samples = nullptr; f->work_cap = 0;
+  CUF(cudaMalloc(&f->work, n * sizeof(WorkItem)));
+  CUF(cudaMalloc(&f->debug_samples, n * sizeof(uint16_t)));
+  f->work_cap = n;
+  return LB_OK;
+}
+
+// classify -> splat -> (closest gather) for one device-resident batch
+int accumulate_device(lb_camera *c, FilterState *f, const lb_samples *S, cudaStream_t stream) {
+  if (S->n == 0) return LB_OK;
+  if (S->n > 0xFFFFFFFFull) return lb_fail(LB_ERR_INVALID, "batch larger than 2^32 samples");
+  int rc = ensure_batch_capacity(f, S->n);
+  if (rc != LB_OK) return rc;
+  FilterConsts fc;
+  fill_consts(c, f, fc);
+  AovSet A;
+  fill_aovs(f, A, S->aov_values);
+  SampleIO io{S->n, S->px, S->py, (const float4 *)S->rgba, (const float4 *)S->pos_cs, (const float4 *)S->raydir,
+              (const float4 *)S->transmission, S->flags, S->inv_density};
+  CUF(cudaMemsetAsync(&f->d_counters->work_count, 0, 2 * sizeof(unsigned), stream));
+  CUF(launch_filter_classify(fc, A, io, f->work, f->d_counters, f->sample_base, stream));
+  CUF(launch_filter_splat(cam_lens_kernel(c), cam_lens(c), cam_consts(c), fc, A, io, f->work, f->d_counters, f->sample_base,
+                          cam_num_sms(c), stream));
+  if (f->has_closest || f->has_debug_closest) CUF(launch_closest_gather(fc, A, io, f->sample_base, stream));
+  f->sample_base += S->n;
+  return LB_OK;
+}
+
+__global__ void k_mask_closest(const unsigned long long *__restrict__ local_key, const unsigned long long *__restrict__ global_key,
+                               float4 *__restrict__ buffer, size_t npx) {
+  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npx) return;
+  if (local_key[p] != global_key[p]) buffer[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+}  // namespace
+
+void filter_state_destroy(FilterState *f) {
+  if (!f) return;
+  if (f->comm) { if (NcclApi *n = load_nccl()) n->CommDestroy(f->comm); }
+  cudaFree(f->block); cudaFree(f->zkey); cudaFree(f->zkey_debug); cudaFree(f->work); cudaFree(f->debug_samples);
+  cudaFree(f->d_counters); cudaFree(f->stage);
+  if (f->stream) cudaStreamDestroy(f->stream);
+  delete f;
+}
+
+extern "C" {
+
+int lb_filter_begin(lb_camera *c, const lb_frame_desc *frame, int n_aov, const lb_aov_desc *aovs) {
+  if (!c || !frame || !aovs || n_aov <= 0 || n_aov > kMaxAov) return lb_fail(LB_ERR_INVALID, "bad filter_begin arguments");
+  if (frame->xres <= 0 || frame->yres <= 0) return lb_fail(LB_ERR_INVALID, "empty frame");
+  std::lock_guard<std::mutex> lk(cam_mutex(c));
+  DeviceGuard g(cam_device(c));
+  FilterState *&slot = cam_filter(c);
+  FilterState *f = slot;
+  if (!f) { f = new FilterState(); slot = f; }
+  f->frame = *frame;
+  f->n_aov = n_aov;
+  memcpy(f->aovs, aovs, n_aov * sizeof(lb_aov_desc));
+  const size_t npx = (size_t)frame->xres * frame->yres;
+  const size_t floats = npx * (4 * (size_t)n_aov + 1);
+  if (floats != f->block_floats) {  // destroy_buffers + reallocate (lentil.h:214,1096-1117)
+    cudaFree(f->block); cudaFree(f->zkey); cudaFree(f->zkey_debug);
+    f->block = nullptr; f->zkey = f->zkey_debug = nullptr;
+    CUF(cudaMalloc(&f->block, floats * sizeof(float)));
+    CUF(cudaMalloc(&f->zkey, npx * sizeof(unsigned long long)));
+    CUF(cudaMalloc(&f->zkey_debug, npx * sizeof(unsigned long long)));
+    f->block_floats = floats;
+  }
+  f->npx = npx;
+  f->has_closest = f->has_debug_closest = false;
+  for (int a = 0; a < n_aov; ++a)
+    if (aovs[a].filter == LB_FILTER_CLOSEST) (aovs[a].role == LB_AOV_LENTIL_DEBUG ? f->has_debug_closest : f->has_closest) = true;
+  CUF(cudaMemset(f->block, 0, floats * sizeof(float)));
+  CUF(cudaMemset(f->zkey, 0xFF, npx * sizeof(unsigned long long)));
+  CUF(cudaMemset(f->zkey_debug, 0xFF, npx * sizeof(unsigned long long)));
+  if (!f->d_counters) CUF(cudaMalloc(&f->d_counters, sizeof(FilterCounters)));
+  CUF(cudaMemset(f->d_counters, 0, sizeof(FilterCounters)));
+  if (!f->stream) CUF(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking));
+  f->sample_base = 0;
+  return LB_OK;
+}
+
+int lb_filter_set_sample_base(lb_camera *c, uint64_t base) {
+  if (!c || !cam_filter(c)) return lb_fail(LB_ERR_STATE, "lb_filter_begin has not been called");
+  cam_filter(c)->sample_base = base;
+  return LB_OK;
+}
+
+int lb_filter_accumulate(lb_camera *c, const lb_samples *S, lb_stream stream) {
+  if (!c || !S) return lb_fail(LB_ERR_INVALID, "null argument");
+  FilterState *f = cam_filter(c);
+  if (!f) return lb_fail(LB_ERR_STATE, "lb_filter_begin has not been called");
+  if (S->n && (!S->px || !S->py || !S->rgba || !S->pos_cs)) return lb_fail(LB_ERR_INVALID, "null sample array");
+  std::lock_guard<std::mutex> lk(cam_mutex(c));
+  DeviceGuard g(cam_device(c));
+  return accumulate_device(c, f, S, (cudaStream_t)stream);
+}
+
+// Host-buffer variant: samples are staged to the device in chunks on the filter's own stream.
+int lb_filter_accumulate_host(lb_camera *c, const lb_samples *S) {
+  if (!c || !S) return lb_fail(LB_ERR_INVALID, "null argument");
+  FilterState *f = cam_filter(c);
+  if (!f) return lb_fail(LB_ERR_STATE, "lb_filter_begin has not been called");
+  if (S->n && (!S->px || !S->py || !S->rgba || !S->pos_cs)) return lb_fail(LB_ERR_INVALID, "null sample array");
+  std::lock_guard<std::mutex> lk(cam_mutex(c));
+  DeviceGuard g(cam_device(c));
+  const size_t chunk = std::min<size_t>(std::max<size_t>(S->n, 1), (size_t)1 << 22);
+  int n_val = 0;
+  for (int a = 0; a < f->n_aov; ++a) if (S->aov_values && S->aov_values[a]) ++n_val;
+  // per-sample bytes: px,py (8) + rgba,pos (32) + raydir,transmission (32) + flags (4) + values
+  const size_t per = 8 + 32 + (S->raydir ? 16 : 0) + (S->transmission ? 16 : 0) + (S->flags ? 4 : 0) + 16 * (size_t)n_val;
+  const size_t need = per * chunk + 256 * 16;
+  if (f->stage_bytes < need) {
+    cudaFree(f->stage); f->stage = nullptr; f->stage_bytes = 0;
+    CUF(cudaMalloc(&f->stage, need));
+    f->stage_bytes = need;
+  }
+  for (size_t base = 0; base < S->n; base += chunk) {
+    const size_t m = std::min(chunk, S->n - base);
+    char *p = f->stage;
+    auto put = [&](const void *src, size_t elem) -> void * {
+      if (!src) return nullptr;
+      void *d = p;
+      cudaMemcpyAsync(d, (const char *)src + base * elem, m * elem, cudaMemcpyHostToDevice, f->stream);
+      p += (chunk * elem + 255) & ~(size_t)255;
+      return d;
+    };
+    lb_samples D = *S;
+    D.n = m;
+    D.rgba = (const float *)put(S->rgba, 16);
+    D.pos_cs = (const float *)put(S->pos_cs, 16);
+    D.raydir = (const float *)put(S->raydir, 16);
+    D.transmission = (const float *)put(S->transmission, 16);
+    const float *vals[kMaxAov] = {nullptr};
+    for (int a = 0; a < f->n_aov; ++a) vals[a] = (S->aov_values && S->aov_values[a]) ? (const float *)put(S->aov_values[a], 16) : nullptr;
+    D.aov_values = vals;
+    D.px = (const int32_t *)put(S->px, 4);
+    D.py = (const int32_t *)put(S->py, 4);
+    D.flags = (const uint32_t *)put(S->flags, 4);
+    CUF(cudaGetLastError());
+    int rc = accumulate_device(c, f, &D, f->stream);
+    if (rc != LB_OK) return rc;
+    CUF(cudaStreamSynchronize(f->stream));  // the staging block is reused by the next chunk
+  }
+  return LB_OK;
+}
+
+int lb_filter_get_stats(lb_camera *c, lb_filter_stats *out) {
+  if (!c || !out) return lb_fail(LB_ERR_INVALID, "null argument");
+  FilterState *f = cam_filter(c);
+  if (!f) return lb_fail(LB_ERR_STATE, "lb_filter_begin has not been called");
+  DeviceGuard g(cam_device(c));
+  CUF(cudaDeviceSynchronize());
+  FilterCounters h;
+  CUF(cudaMemcpy(&h, f->d_counters, sizeof h, cudaMemcpyDeviceToHost));
+  out->samples = h.samples; out->redistributed = h.redistributed; out->splats = h.splats;
+  out->attempts = h.attempts; out->passthrough = h.passthrough;
+  return LB_OK;
+}
+
+int lb_filter_newton_iterations(lb_camera *c, uint64_t *out) {  // diagnostic: lt_sample_aperture iterations so far
+  FilterState *f = c ? cam_filter(c) : nullptr;
+  if (!f || !out) return lb_fail(LB_ERR_STATE, "lb_filter_begin has not been called");
+  DeviceGuard g(cam_device(c));
+  CUF(cudaDeviceSynchronize());
+  FilterCounters h;
+  CUF(cudaMemcpy(&h, f->d_counters, sizeof h, cudaMemcpyDeviceToHost));
+  *out = h.newton_its;
+  return LB_OK;
+}
+
+int lb_imager_resolve(lb_camera *c, int aov, int x0, int y0, int w, int h, float *rgba_out, lb_stream stream) {
+  if (!c || !rgba_out) return lb_fail(LB_ERR_INVALID, "null argument");
+  FilterState *f = cam_filter(c);
+  if (!f) return lb_fail(LB_ERR_STATE, "lb_filter_begin has not been called");
+  if (aov < 0 || aov >= f->n_aov) return lb_fail(LB_ERR_INVALID, "aov index out of range");
+  const int rx = x0 - f->frame.region_min_x, ry = y0 - f->frame.region_min_y;
+  if (rx < 0 || ry < 0 || w < 0 || h < 0 || rx + w > f->frame.xres || ry + h > f->frame.yres) return lb_fail(LB_ERR_INVALID, "bucket outside the region");
+  DeviceGuard g(cam_device(c));
+  CUF(launch_resolve((const float4 *)(f->block + (size_t)aov * f->npx * 4), f->block + (size_t)f->n_aov * f->npx * 4, f->aovs[aov].filter,
+                     f->aovs[aov].role, f->frame.xres, rx, ry, w, h, (float4 *)rgba_out, (cudaStream_t)stream));
+  return LB_OK;
+}
+
+int lb_imager_resolve_host(lb_camera *c, int aov, int x0, int y0, int w, int h, float *rgba_out) {
+  if (!c || !rgba_out) return lb_fail(LB_ERR_INVALID, "null argument");
+  FilterState *f = cam_filter(c);
+  if (!f) return lb_fail(LB_ERR_STATE, "lb_filter_begin has not been called");
+  DeviceGuard g(cam_device(c));
+  float *d = nullptr;
+  const size_t bytes = (size_t)std::max(w, 0) * std::max(h, 0) * 16;
+  if (bytes == 0) return LB_OK;
+  CUF(cudaMalloc(&d, bytes));
+  int rc = lb_imager_resolve(c, aov, x0, y0, w, h, d, f->stream);
+  if (rc == LB_OK) {
+    cudaError_t e = cudaMemcpyAsync(rgba_out, d, bytes, cudaMemcpyDeviceToHost, f->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(f->stream);
+    if (e != cudaSuccess) rc = lb_fail(LB_ERR_CUDA, cudaGetErrorString(e));
+  }
+  cudaFree(d);
+  return rc;
+}
+
+int lb_filter_buffers(lb_camera *c, int aov, float **buffer, float **weight) {
+  FilterState *f = c ? cam_filter(c) : nullptr;
+  if (!f) return lb_fail(LB_ERR_STATE, "lb_filter_begin has not been called");
+  if (aov < 0 || aov >= f->n_aov) return lb_fail(LB_ERR_INVALID, "aov index out of range");
+  if (buffer) *buffer = f->block + (size_t)aov * f->npx * 4;
+  if (weight) *weight = f->block + (size_t)f->n_aov * f->npx * 4;
+  return LB_OK;
+}
+
+int lb_filter_buffers_host(lb_camera *c, int aov, float *buffer_out, float *weight_out) {
+  FilterState *f = c ? cam_filter(c) : nullptr;
+  if (!f) return lb_fail(LB_ERR_STATE, "lb_filter_begin has not been called");
+  if (aov < 0 || aov >= f->n_aov) return lb_fail(LB_ERR_INVALID, "aov index out of range");
+  DeviceGuard g(cam_device(c));
+  CUF(cudaDeviceSynchronize());
+  if (buffer_out) CUF(cudaMemcpy(buffer_out, f->block + (size_t)aov * f->npx * 4, f->npx * 16, cudaMemcpyDeviceToHost));
+  if (weight_out) CUF(cudaMemcpy(weight_out, f->block + (size_t)f->n_aov * f->npx * 4, f->npx * 4, cudaMemcpyDeviceToHost));
+  return LB_OK;
+}
+
+// ---- multi-GPU ------------------------------------------------------------------------------------
+int lb_comm_unique_id(uint8_t id_out[128]) {
+  NcclApi *n = load_nccl();
+  if (!n) return lb_fail(LB_ERR_COMM, "libnccl.so.2 not found (set LB_NCCL_LIB)");
+  ncclUniqueId id;
+  if (n->GetUniqueId(&id) != ncclSuccess) return lb_fail(LB_ERR_COMM, "ncclGetUniqueId failed");
+  memcpy(id_out, id.internal, 128);
+  return LB_OK;
+}
+
+int lb_comm_init(lb_camera *c, int world_size, int rank, const uint8_t id_in[128]) {
+  FilterState *f = c ? cam_filter(c) : nullptr;
+  if (!f) return lb_fail(LB_ERR_STATE, "lb_filter_begin has not been called");
+  NcclApi *n = load_nccl();
+  if (!n) return lb_fail(LB_ERR_COMM, "libnccl.so.2 not found (set LB_NCCL_LIB)");
+  DeviceGuard g(cam_device(c));
+  if (f->comm) { n->CommDestroy(f->comm); f->comm = nullptr; }
+  ncclUniqueId id;
+  memcpy(id.internal, id_in, 128);
+  ncclResult_t r = n->CommInitRank(&f->comm, world_size, id, rank);
+  if (r != ncclSuccess) return lb_fail(LB_ERR_COMM, n->GetErrorString ? n->GetErrorString(r) : "ncclCommInitRank failed");
+  f->world = world_size;
+  f->rank = rank;
+  return LB_OK;
+}
+
+int lb_filter_reduce(lb_camera *c, int root, lb_stream stream_) {
+  FilterState *f = c ? cam_filter(c) : nullptr;
+  if (!f) return lb_fail(LB_ERR_STATE, "lb_filter_begin has not been called");
+  if (f->world <= 1 || !f->comm) return LB_OK;  // single rank: nothing to combine
+  NcclApi *n = load_nccl();
+  if (!n) return lb_fail(LB_ERR_COMM, "NCCL unavailable");
+  DeviceGuard g(cam_device(c));
+  cudaStream_t stream = (cudaStream_t)stream_;
+  auto check = [&](ncclResult_t r) { return r == ncclSuccess ? LB_OK : lb_fail(LB_ERR_COMM, n->GetErrorString ? n->GetErrorString(r) : "nccl error"); };
+  int rc;
+  // closest AOVs: global min of the depth keys, then every rank but the winner clears its pixel
+  for (int pass = 0; pass < 2; ++pass) {
+    const bool on = pass == 0 ? f->has_closest : f->has_debug_closest;
+    if (!on) continue;
+    unsigned long long *local = pass == 0 ? f->zkey : f->zkey_debug;
+    unsigned long long *global = nullptr;
+    CUF(cudaMallocAsync(&global, f->npx * sizeof(unsigned long long), stream));
+    if ((rc = check(n->AllReduce(local, global, f->npx, ncclUint64, ncclMin, f->comm, stream))) != LB_OK) return rc;
+    for (int a = 0; a < f->n_aov; ++a) {
+      const bool dbg = f->aovs[a].role == LB_AOV_LENTIL_DEBUG;
+      if (f->aovs[a].filter != LB_FILTER_CLOSEST || dbg != (pass == 1)) continue;
+      k_mask_closest<<<(unsigned)((f->npx + 255) / 256), 256, 0, stream>>>(local, global, (float4 *)(f->block + (size_t)a * f->npx * 4), f->npx);
+    }
+    CUF(cudaMemcpyAsync(local, global, f->npx * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, stream));
+    CUF(cudaFreeAsync(global, stream));
+  }
+  // one sum-reduce over every AOV plane + the weight plane
+  if (root < 0) rc = check(n->AllReduce(f->block, f->block, f->block_floats, ncclFloat32, ncclSum, f->comm, stream));
+  else rc = check(n->Reduce(f->block, f->block, f->block_floats, ncclFloat32, ncclSum, root, f->comm, stream));
+  return rc;
+}
+
+int lb_comm_destroy(lb_camera *c) {
+  FilterState *f = c ? cam_filter(c) : nullptr;
+  if (!f || !f->comm) return LB_OK;
+  if (NcclApi *n = load_nccl()) n->CommDestroy(f->comm);
+  f->comm = nullptr;
+  f->world = 1;
+  return LB_OK;
+}
+
+}  // extern "C"

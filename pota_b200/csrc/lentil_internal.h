@@ -1,0 +1,91 @@
+// lentil_internal.h — host-visible launchers of the CUDA kernels (internal to liblentil_b200.so).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "lens_table.h"
+
+namespace lb {
+
+struct RayIO;
+
+// ---- K1 (camera_kernels.cu) -------------------------------------------------------------------
+// lens_kernel < 0: table-driven evaluator; otherwise the unrolled kernel of that LensModel.
+cudaError_t launch_create_rays(int lens_kernel, const LensTable &lens, const CamConsts<float> &cam, const RayIO &io, size_t n,
+                               uint64_t ray_id_base, cudaStream_t stream);
+bool has_unrolled_kernel(int lens_model);
+cudaError_t launch_reverse_rays(size_t n, const float4 *Po, float2 *Ps, float tan_fov, cudaStream_t stream);
+
+// ---- setup solvers, FP64 (setup_kernels.cu) -----------------------------------------------------
+// camera_get_y0_intersection_distance (lentil.h:1361-1386) for n sensor shifts.
+// out[i] = {intersection z, transmittance, out_x^2+out_y^2, inner-pupil r^2}
+cudaError_t launch_focus_distances(const LensTable &lens, const CamConsts<double> &cam, double aperture_y, const double *shifts,
+                                   int n, double4 *out, cudaStream_t stream);
+// trace_backwards_for_fstop (lentil.h:1390-1441): for i in [1, n): out[i] = {valid, pos.y, pos.z, 0}
+cudaError_t launch_fstop_rays(const LensTable &lens, const CamConsts<double> &cam, int n, double outer_pupil_radius, double4 *out,
+                              cudaStream_t stream);
+
+// ---- K2/K3 (filter_kernels.cu) ------------------------------------------------------------------
+struct FilterConsts {
+  int32_t xres, yres, xres_full, yres_full, region_min_x, region_min_y;
+  int32_t n_aov;
+  int32_t bidir_sample_mult;
+  int32_t camera_type;
+  int32_t enable_skydome, enable_bidir_transmission;
+  float unit_mult;            // 0.1, 1, 10, 100 (lentil_filter.cpp:143-148)
+  float focal_length;         // thin-lens focal length param (get_coc_thinlens)
+  float coc_focus_distance;   // (float)focus_distance, /10 for PO (lentil.h:676-681)
+  float coc_aperture_radius;  // (float)aperture_radius, *10 for thin lens
+  float bidir_add_energy, bidir_add_energy_transition;
+  double bidir_add_energy_minimum_luminance;
+  float abb_chromatic;
+  double lens_length_tenth;   // lens_length * 0.1 (lentil_filter.cpp:240)
+  double sensor_half;         // sensor_width * 0.5
+  double aspect_full;         // xres_without_region / yres_without_region
+};
+
+constexpr int kMaxAov = 16;
+struct AovSet {
+  float4 *buffer[kMaxAov];         // AOVData::buffer
+  const float4 *values[kMaxAov];   // per-sample values of this batch (NULL: use rgba / lentil_debug)
+  int32_t filter[kMaxAov];
+  int32_t role[kMaxAov];
+  float *weight;                   // filter_weight_buffer
+  unsigned long long *zkey;        // closest-filter depth|~sample key per pixel
+  unsigned long long *zkey_debug;
+  uint16_t *debug_samples;         // per-sample `samples * redistribute` of this batch (closest lentil_debug AOV only)
+};
+
+struct SampleIO {
+  size_t n;
+  const int32_t *px, *py;
+  const float4 *rgba, *pos_cs, *raydir, *transmission;
+  const uint32_t *flags;
+  float inv_density;
+};
+
+struct WorkItem {  // one redistributed source sample
+  uint32_t sample;
+  uint32_t n_samples;  // clamp(ceil(coc^2 * ...), 4, 2000)
+  float add_energy;    // fitted_bidir_add_energy
+  float csp[3];        // camera-space position after unit scaling / skydome substitution (lentil_filter.cpp:121-148)
+};
+
+struct FilterCounters {  // device-side mirror of lb_filter_stats + work queue heads
+  unsigned long long samples, redistributed, splats, attempts, passthrough;
+  unsigned long long newton_its;
+  unsigned int work_count, work_next;
+};
+
+cudaError_t launch_filter_classify(const FilterConsts &fc, const AovSet &aovs, const SampleIO &s, WorkItem *work,
+                                   FilterCounters *counters, uint64_t sample_base, cudaStream_t stream);
+cudaError_t launch_filter_splat(int lens_kernel, const LensTable &lens, const CamConsts<float> &cam, const FilterConsts &fc,
+                                const AovSet &aovs, const SampleIO &s, const WorkItem *work, FilterCounters *counters,
+                                uint64_t sample_base, int num_sms, cudaStream_t stream);
+cudaError_t launch_closest_gather(const FilterConsts &fc, const AovSet &aovs, const SampleIO &s, uint64_t sample_base,
+                                  cudaStream_t stream);
+cudaError_t launch_resolve(const float4 *buffer, const float *weight, int filter, int role, int xres, int x0, int y0, int w, int h,
+                           float4 *out, cudaStream_t stream);
+
+}  // namespace lb

@@ -1,0 +1,131 @@
+"""Synthetic inputs of the BASELINE.json configs, built with torch so the same code
+runs on the CPU (tests, oracle) and on the GPU (bench).  The jitter / lens samples come from the
+reference's own counter RNG, tea<8> + LCG (/root/reference/src/global.h:32-57), restated here on
+64-bit integer tensors (bit-exact, checked against the oracle in tests/test_workloads.py).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+M32 = 0xFFFFFFFF
+
+
+def tea8(v0: torch.Tensor, v1: torch.Tensor) -> torch.Tensor:
+    """tea<8>(val0, val1) on int64 tensors holding uint32 values."""
+    v0 = v0.to(torch.int64) & M32
+    v1 = v1.to(torch.int64) & M32
+    s0 = 0
+    for _ in range(8):
+        s0 = (s0 + 0x9E3779B9) & M32
+        v0 = (v0 + ((((v1 << 4) + 0xA341316C) & M32) ^ ((v1 + s0) & M32) ^ (((v1 >> 5) + 0xC8013EA4) & M32))) & M32
+        v1 = (v1 + ((((v0 << 4) + 0xAD90777D) & M32) ^ ((v0 + s0) & M32) ^ (((v0 >> 5) + 0x7E95761E) & M32))) & M32
+    return v0
+
+
+def lcg(state: torch.Tensor):
+    """rng(previous): returns (new_state, float32 in [0,1))."""
+    state = (state * 1664525 + 1013904223) & M32
+    return state, (state & 0x00FFFFFF).to(torch.float32) / 16777216.0
+
+
+def camera_samples(width: int, height: int, spp: int, device="cpu", first: int = 0, count: int | None = None, seed_mode: str = "pixel"):
+    """AtCameraInput arrays for a width x height x spp frame (configs C1/C2).
+
+    Sample index k = (py*width + px)*spp + s.  seed_mode "pixel": seed = tea<8>(py*width+px, s) (C2);
+    "linear": seed = tea<8>(k, 0x5EED) (C1, spp = 1).  Returns dict of float32 [n] tensors.
+    """
+    total = width * height * spp
+    count = total - first if count is None else count
+    k = torch.arange(first, first + count, dtype=torch.int64, device=device)
+    pix = k // spp
+    s = k % spp
+    px = pix % width
+    py = pix // width
+    seed = tea8(pix, s) if seed_mode == "pixel" else tea8(k, torch.full_like(k, 0x5EED))
+    seed, jx = lcg(seed)
+    seed, jy = lcg(seed)
+    seed, lensx = lcg(seed)
+    seed, lensy = lcg(seed)
+    aspect = width / height
+    sx = 2.0 * (px.to(torch.float32) + jx) / width - 1.0
+    sy = (1.0 - 2.0 * (py.to(torch.float32) + jy) / height) / aspect
+    d = torch.full_like(sx, 2.0 / width)
+    return dict(sx=sx.contiguous(), sy=sy.contiguous(), dsx=d, dsy=d.clone(), lensx=lensx.contiguous(), lensy=lensy.contiguous())
+
+
+def highlight_frame(width: int, height: int, spp: int, tan_fov: float, device="cpu", first: int = 0, count: int | None = None,
+                    z_plane: float = 75.0, pitch: float = 5.4, radius: float = 0.133, grid=(16, 12), radiance: float = 84.1589,
+                    n_extra_aov: int = 0):
+    """Synthetic HDR frame of config C3, modelled on /root/reference/tests/cuda/lightgrid.ass: a black
+    background at Z = inf plus a grid of emissive discs on the plane z_cs = -z_plane.  One sample per
+    (pixel, s); the sample position comes from a pinhole ray through the jittered pixel position.
+
+    Returns dict(px, py int32 [n]; rgba, pos_cs float32 [n,4]; aov_values list of [n,4]).
+    """
+    total = width * height * spp
+    count = total - first if count is None else count
+    k = torch.arange(first, first + count, dtype=torch.int64, device=device)
+    pix = k // spp
+    s = k % spp
+    px = pix % width
+    py = pix // width
+    seed = tea8(pix, s + 0x1000)
+    seed, jx = lcg(seed)
+    seed, jy = lcg(seed)
+    aspect = width / height
+    sx = 2.0 * (px.to(torch.float32) + jx) / width - 1.0
+    sy = (1.0 - 2.0 * (py.to(torch.float32) + jy) / height) / aspect
+    x = sx * (tan_fov * z_plane)
+    y = sy * (tan_fov * z_plane)
+    # nearest disc centre of the grid (centred on the axis)
+    gx, gy = grid
+    cx = (torch.clamp(torch.round(x / pitch + (gx - 1) / 2.0), 0, gx - 1) - (gx - 1) / 2.0) * pitch
+    cy = (torch.clamp(torch.round(y / pitch + (gy - 1) / 2.0), 0, gy - 1) - (gy - 1) / 2.0) * pitch
+    hit = ((x - cx) ** 2 + (y - cy) ** 2) <= radius * radius
+    n = count
+    rgba = torch.zeros((n, 4), dtype=torch.float32, device=device)
+    rgba[hit, 0:3] = radiance
+    rgba[hit, 3] = 1.0
+    pos = torch.zeros((n, 4), dtype=torch.float32, device=device)
+    pos[:, 3] = 1.0e30  # AI_INFINITE: background is never redistributed (lentil_filter.cpp:130-133)
+    pos[hit, 0] = x[hit]
+    pos[hit, 1] = y[hit]
+    pos[hit, 2] = -z_plane
+    pos[hit, 3] = torch.sqrt(x[hit] ** 2 + y[hit] ** 2 + z_plane**2)
+    out = dict(px=px.to(torch.int32).contiguous(), py=py.to(torch.int32).contiguous(), rgba=rgba, pos_cs=pos)
+    # per-light AOVs (config C5): light l owns the discs with (column + row) % n_extra == l
+    extra = []
+    if n_extra_aov:
+        col = torch.round(cx / pitch + (gx - 1) / 2.0).to(torch.int64)
+        row = torch.round(cy / pitch + (gy - 1) / 2.0).to(torch.int64)
+        owner = (col + row) % n_extra_aov
+        for l in range(n_extra_aov):
+            a = torch.zeros((n, 4), dtype=torch.float32, device=device)
+            m = hit & (owner == l)
+            a[m] = rgba[m]
+            extra.append(a)
+    out["aov_values"] = extra
+    return out
+
+
+def disc_bokeh_image(size: int = 64):
+    """A small procedural bokeh kernel (ring + hot centre), float32 [size, size, 3] in [0,1]."""
+    import numpy as np
+
+    yy, xx = np.mgrid[0:size, 0:size].astype(np.float32)
+    c = (size - 1) / 2.0
+    r = np.sqrt((xx - c) ** 2 + (yy - c) ** 2) / c
+    lum = np.where(r <= 1.0, 0.35 + 0.65 * np.exp(-((r - 0.85) ** 2) / 0.01) + 0.3 * np.exp(-(r**2) / 0.02), 0.0).astype(np.float32)
+    return np.repeat(lum[:, :, None], 3, axis=2).astype(np.float32)
+
+
+def camera_ray_flops(work, newton_its_per_trace: float, traces_per_ray: float = 3.0) -> float:
+    """per forward trace k*(F_ap + 16) + F_eval + 60 flop."""
+    return traces_per_ray * (newton_its_per_trace * (work.F_ap + 16.0) + work.F_eval + 60.0)
+
+
+def reverse_attempt_flops(work, newton_its: float) -> float:
+    """per reverse attempt k*(F_apxy + F_apJ + F_out4 + F_outJ + 120) + F_T flop."""
+    return newton_its * (work.F_apxy + work.F_apJ + work.F_out4 + work.F_outJ + 120.0) + work.F_T
