@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the lentil hot paths on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
+
+Prints ONE JSON line.  Headline metric (BASELINE.json configs[1]): camera rays/s for a 3840x2160 x 64 spp
+frame, one lens, fixed f-stop/focus.  A "step" is one pass of camera_create_ray over that frame
+(530 841 600 rays = 1 592 524 800 forward traces).  `value` is measured with inputs and outputs
+resident in HBM; `e2e` drives the same frame through the host-buffer C-ABI call (pinned host memory,
+H2D and D2H inside the timed region).  The secondary object `splat` reports the redistribution path
+(configs[2]: 1920x1080, 16 spp, image-bokeh kernel) in splats/s.
+
+N > 1: one process per GPU.  Camera rays shard with no collective (every rank traces its own frame's
+worth of samples, weak scaling); the splat frame is split by sample range and combined with
+lb_filter_reduce (NCCL over NVLink).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+from pota_b200 import abi, workloads  # noqa: E402
+
+FRAME_W, FRAME_H, FRAME_SPP = 3840, 2160, 64
+SPLAT_W, SPLAT_H, SPLAT_SPP = 1920, 1080, 16
+SPLAT_GRID = (8, 4)  # discs whose bokeh stays inside the frame (out-of-frame splats burn 5x attempts, lentil_filter.cpp:282-287)
+LENS_MODEL = 5  # asahi__takumar__1969__50mm stand-in: the pack's double-Gauss 50 mm
+CHUNK_RAYS = FRAME_W * FRAME_H * 4  # 33 177 600 rays per call on the e2e path (4 spp of the frame)
+IN_KEYS = ("sx", "sy", "dsx", "dsy", "lensx", "lensy")
+
+
+def camera_params():
+    return abi.CameraParams.defaults(camera_type=abi.LB_CAMERA_POLYNOMIAL_OPTICS, lens_model=LENS_MODEL, fstop=2.8, focus_dist=150.0)
+
+
+def splat_params():
+    return abi.CameraParams.defaults(camera_type=abi.LB_CAMERA_POLYNOMIAL_OPTICS, lens_model=LENS_MODEL, fstop=1.4, focus_dist=35.0,
+                                     bidir_sample_mult=10, bokeh_enable_image=1)
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons every 200 ms while the timed region runs."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+def cpu_camera_baseline(nthreads: int, n_rays: int):
+    """Oracle (CPU restatement of the reference) on a bounded sample of the same frame."""
+    from oracle import orc
+
+    cam = orc.OracleCamera(camera_params())
+    # a strided sample of whole-frame pixels, 1 spp each, so that the sample covers the sensor like the frame does
+    ins = workloads.camera_samples(FRAME_W // 4, FRAME_H // 4, 1, "cpu", 0, n_rays, "linear")
+    arrs = [ins[k].numpy() for k in IN_KEYS]
+    t0 = time.perf_counter()
+    out = cam.create_rays(*arrs, nthreads=nthreads)
+    dt = time.perf_counter() - t0
+    c = cam.counters()
+    return dict(rays_per_s=n_rays / dt, seconds=dt, newton_its_per_trace=c["fw_newton_its"] / max(c["fw_traces"], 1),
+                traces_per_ray=c["fw_traces"] / n_rays, dead_fraction=float((out["weight"][0] == 0).mean()))
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path on the host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    nthreads = os.cpu_count() or 1
+    n = 40_000 * nthreads  # bounded sample per step (~4 s of CPU work)
+    times = []
+    for i in range(args.warmup + args.steps):
+        r = cpu_camera_baseline(nthreads, n)
+        if i >= args.warmup:
+            times.append(r["seconds"])
+    v = n / float(np.mean(times))
+    sample = f"{n} rays per step sampled over the 3840x2160 frame (1 per 16 pixels), {nthreads} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": "camera_rays_per_s", "value": v, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": float(np.mean(times)) * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "camera_create_ray 3840x2160x64spp, asahi__takumar__1969__50mm (pack double-Gauss 50mm), f/2.8, focus 150cm",
+                   "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "rays/s", "cores": nthreads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frame-scale", type=float, default=1.0, help="debug: scale the spp of both workloads")
+    ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-splat", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from pota_b200.camera import RAY_OUT_FIELDS, Camera, lib
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU path)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    spp = max(1, int(round(FRAME_SPP * args.frame_scale)))
+    n_rays = FRAME_W * FRAME_H * spp
+    cam = Camera(camera_params(), device=local_rank)
+    work = cam.lens_work
+
+    # ---- device-resident frame: inputs generated on the device chunk by chunk ----------------------
+    ins = {k: torch.empty(n_rays, dtype=torch.float32, device=dev) for k in IN_KEYS}
+    first_sample = rank * n_rays  # every rank traces its own frame's worth of samples (weak scaling)
+    gen = FRAME_W * FRAME_H
+    for s0 in range(0, n_rays, gen):
+        m = min(gen, n_rays - s0)
+        c = workloads.camera_samples(FRAME_W, FRAME_H, spp * world, dev, first_sample + s0, m, "pixel")
+        for k in IN_KEYS:
+            ins[k][s0:s0 + m] = c[k]
+        del c
+    out = {k: torch.empty((3, n_rays), dtype=torch.float32, device=dev) for k in RAY_OUT_FIELDS}
+    stream = torch.cuda.current_stream()
+
+    def step_device():
+        cam.create_rays(*[ins[k] for k in IN_KEYS], ray_id_base=first_sample, out=out, stream=stream)
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    with ClockSampler(local_rank) as clocks:
+        ev[0].record(stream)
+        for i in range(args.steps):
+            step_device()
+            ev[i + 1].record(stream)
+        barrier()
+    step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    total_s = max_over_ranks(sum(step_ms) * 1e-3)
+    value = world * n_rays * args.steps / total_s
+    kernel_ms = float(np.mean(step_ms))
+    dead = float((out["weight"][0, : 1 << 22] == 0).float().mean().item())
+    clock_summary = clocks.summary()
+
+    # ---- e2e: same frame through the host-buffer C-ABI call -------------------------------------------
+    e2e = None
+    if not args.skip_e2e:
+        chunk = min(CHUNK_RAYS, n_rays)
+        h_in = {k: torch.empty(chunk, dtype=torch.float32).pin_memory() for k in IN_KEYS}
+        h_out = {k: torch.empty((3, chunk), dtype=torch.float32).pin_memory() for k in RAY_OUT_FIELDS}
+        for k in IN_KEYS:
+            h_in[k].copy_(ins[k][:chunk])
+        calls = -(-n_rays // chunk)
+
+        def step_host():
+            for cidx in range(calls):
+                m = min(chunk, n_rays - cidx * chunk)
+                cam.create_rays_host(*[h_in[k][:m] for k in IN_KEYS], out={k: h_out[k] for k in RAY_OUT_FIELDS} if m == chunk else
+                                     {k: h_out[k] for k in RAY_OUT_FIELDS}, ray_id_base=first_sample + cidx * chunk)
+
+        # warm-up (allocates the staging ring) doubling as a check: the host path must reproduce the device path bit for bit
+        cam.create_rays_host(*[h_in[k] for k in IN_KEYS], out=h_out, ray_id_base=first_sample)
+        checked = all(bool(torch.equal(h_out[k].to(dev), out[k][:, :chunk])) for k in ("origin", "dir", "dDdx", "weight"))
+        assert checked, "host path and device path disagree"
+        barrier()
+        t0 = time.perf_counter()
+        e2e_steps = max(1, min(args.steps, 2))
+        for _ in range(e2e_steps):
+            for cidx in range(calls):
+                m = min(chunk, n_rays - cidx * chunk)
+                cam.create_rays_host(*[h_in[k][:m] for k in IN_KEYS], out=h_out, ray_id_base=first_sample + cidx * chunk)
+        barrier()
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        e2e = {"value": world * n_rays * e2e_steps / e2e_s, "unit": "rays/s", "h2d_bytes_per_step": n_rays * 24, "d2h_bytes_per_step": n_rays * 84,
+               "ms_per_step": e2e_s / e2e_steps * 1e3, "calls_per_step": calls, "host_memory": "pinned", "matches_device_path": checked}
+        del h_in, h_out
+    del ins, out
+    torch.cuda.empty_cache()
+
+    # ---- roofline of the dominant kernel -------------------------------------------------------------
+    peak = __import__("ctypes").c_double()
+    lib().lb_bench_fp32_peak(local_rank, __import__("ctypes").byref(peak))
+    cpu = None
+    k_its, traces_per_ray = 4.0, 3.0
+    if rank == 0 and not args.skip_cpu:
+        nthreads = os.cpu_count() or 1
+        cpu = cpu_camera_baseline(nthreads, 40_000 * nthreads)
+        k_its, traces_per_ray = cpu["newton_its_per_trace"], cpu["traces_per_ray"]
+    flop_per_ray = workloads.camera_ray_flops(work, k_its, traces_per_ray)
+    achieved_tflops = flop_per_ray * n_rays / (kernel_ms * 1e-3) / 1e12
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except OSError:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    roofline = {"bound": "fp32", "achieved": achieved_tflops, "peak": peak.value, "unit": "TFLOP/s", "frac": achieved_tflops / max(peak.value, 1e-9),
+                "traffic": None, "peak_source": "lb_bench_fp32_peak (register FFMA chains) measured in this run; nominal 148*128*2*1.965 GHz = 74.5",
+                "flop_per_ray": flop_per_ray, "newton_its_per_trace": k_its, "traces_per_ray": traces_per_ray,
+                "hbm": {"achieved": n_rays * 108 / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": n_rays * 108 / (kernel_ms * 1e-3) / 1e9 / hbm_peak, "bytes_per_ray": 108,
+                        "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"}}
+
+    # ---- secondary: redistribution (configs[2]) --------------------------------------------------------
+    splat = None
+    launches = args.steps
+    if not args.skip_splat:
+        splat = bench_splat(args, rank, world, local_rank, dev, barrier, max_over_ranks, sum_over_ranks)
+
+    if rank == 0:
+        line = {
+            "metric": "camera_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"camera_create_ray {FRAME_W}x{FRAME_H}x{spp}spp per GPU ({n_rays} rays = {3 * n_rays} forward traces), "
+                                   "asahi__takumar__1969__50mm (pack double-Gauss 50mm), f/2.8, focus 150cm",
+                       "l2": "inputs (12.7 GB) and outputs (44.6 GB) exceed L2, no flush needed", "kernel": cam.kernel_kind,
+                       "dead_ray_fraction": dead},
+            "e2e": e2e, "gpu_launches": launches, "clocks": clock_summary, "roofline": roofline,
+            "cpu_baseline": None if cpu is None else {"value": cpu["rays_per_s"], "unit": "rays/s", "cores": os.cpu_count(), "kind": "port",
+                                                     "sample": f"{40_000 * (os.cpu_count() or 1)} rays sampled over the frame, oracle (FP64 restatement of lentil.h), all host threads"},
+            "splat": splat,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_splat(args, rank, world, local_rank, dev, barrier, max_over_ranks, sum_over_ranks):
+    import torch
+    import torch.distributed as dist
+
+    from pota_b200.camera import Camera
+
+    spp = max(1, int(round(SPLAT_SPP * args.frame_scale)))
+    cam = Camera(splat_params(), bokeh=workloads.disc_bokeh_image(250), device=local_rank)
+    total = SPLAT_W * SPLAT_H * spp
+    lo, hi = total * rank // world, total * (rank + 1) // world  # strong scaling: the frame's samples are split by range
+    fr = workloads.highlight_frame(SPLAT_W, SPLAT_H, spp, cam.state.tan_fov, dev, lo, hi - lo, grid=SPLAT_GRID)
+    aovs = [("RGBA", abi.LB_FILTER_GAUSSIAN, abi.LB_AOV_RGBA)]
+    cam.filter_begin(SPLAT_W, SPLAT_H, aovs)
+    if world > 1:
+        uid = [Camera.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        cam.comm_init(world, rank, uid[0])
+    stream = torch.cuda.current_stream()
+
+    def step():
+        cam.filter_begin(SPLAT_W, SPLAT_H, aovs)
+        cam.filter_accumulate(fr["px"], fr["py"], fr["rgba"], fr["pos_cs"], 1.0 / spp, stream=stream)
+        if world > 1:
+            cam.filter_reduce(root=0, stream=stream)
+        return cam.resolve(0, stream=stream)
+
+    steps = max(1, min(args.steps, 3))
+    step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        img = step()
+    e1.record(stream)
+    barrier()
+    s = max_over_ranks(e0.elapsed_time(e1) * 1e-3) / steps
+    st = cam.filter_stats()
+    splats = sum_over_ranks(float(st["splats"]))
+    attempts = sum_over_ranks(float(st["attempts"]))
+    its = sum_over_ranks(float(st["newton_its"]))
+    w = cam.lens_work
+    flop = its * (w.F_apxy + w.F_apJ + w.F_out4 + w.F_outJ + 120.0) + attempts * w.F_T
+    return {"metric": "redistributed_splats_per_s", "value": splats / s, "unit": "splats/s", "ms_per_step": s * 1e3, "scaling": "strong",
+            "config": {"workload": f"bidirectional redistribution {SPLAT_W}x{SPLAT_H}x{spp}spp synthetic highlight frame, 250x250 image-bokeh kernel, "
+                                   f"{SPLAT_GRID[0]}x{SPLAT_GRID[1]} emissive discs at z=-75, f/1.4 focus 35, bidir_sample_mult 10, 1 RGBA AOV"},
+            "splats_per_step": splats, "attempts_per_step": attempts, "newton_its_per_attempt": its / max(attempts, 1.0),
+            "source_samples": SPLAT_W * SPLAT_H * spp, "tflops_algorithmic": flop / s / 1e12,
+            "image_energy": float(img[..., :3].sum().item())}
+
+
+if __name__ == "__main__":
+    main()

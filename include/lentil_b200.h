@@ -168,6 +168,10 @@ typedef struct lb_lens_work {
   double F_T;      /* transmittance polynomial */
 } lb_lens_work;
 LB_API int lb_camera_lens_work(const lb_camera *cam, lb_lens_work *out);
+/* 1 when the camera's lens runs the per-lens unrolled kernels, 0 for the table-driven kernels. */
+LB_API int lb_camera_kernel_kind(const lb_camera *cam);
+/* On-box FP32 FMA throughput in TFLOP/s (register-operand FFMA chains): roofline denominator. */
+LB_API int lb_bench_fp32_peak(int device, double *tflops_out);
 
 /* ---- filter / imager ---------------------------------------------------------------------- */
 

@@ -33,6 +33,7 @@ UNITS = {
     "filter_classify.cu": ["-fmad=false"],
     "lentil_host.cu": [],
     "filter_host.cu": ["-I", "/usr/include"],
+    "microbench.cu": [],
 }
 
 

@@ -47,8 +47,9 @@ LB_DEV FwRay trace_ray_fw_po(const E &ev, const CamConsts<float> &cam, float sx,
     y += dy * cam.sensor_shift;
     const float b[5] = {x, y, dx, dy, cam.lambda};
     out[0] = out[1] = out[2] = out[3] = 0.f;  // `out.setZero()` at loop top: a failed last try leaves the evaluated values
-    ev.out4(b, out);
-    const float transmittance = fmaxf(0.f, ev.transmittance(b));
+    float tr;
+    ev.out5(b, out, tr);
+    const float transmittance = fmaxf(0.f, tr);
     if (transmittance <= 0.f) { ++tries; continue; }
     if (out[0] * out[0] + out[1] * out[1] > cam.outer_pupil_r2) { ++tries; continue; }
     const float px = x + dx * cam.bfl, py = y + dy * cam.bfl;
@@ -79,13 +80,21 @@ LB_DEV void camera_create_ray(const E &ev, const CamConsts<float> &cam, const Ra
   float r1 = __ldg(io.lensx + i), r2 = __ldg(io.lensy + i);
   const uint32_t ray_id = (uint32_t)(ray_id_base + i);
   const float step = 0.001f;
-  int tries, tries_d;
-  const FwRay m = trace_ray_fw_po(ev, cam, sx, sy, r1, r2, false, ray_id, tries);
+  int tries = 0;
   // differential rays: baseline `step` of the reference, optionally stretched ("differentials")
   const float fd = step * cam.deriv_baseline;
   const float sx_dx = sx + (dsx * fd), sy_dy = sy + (dsy * fd);
-  const FwRay ax = trace_ray_fw_po(ev, cam, sx_dx, sy, r1, r2, true, ray_id, tries_d);
-  const FwRay ay = trace_ray_fw_po(ev, cam, sx, sy_dy, r1, r2, true, ray_id, tries_d);
+  // main ray, then the two differential rays (lentil_camera.cpp:93,111-112) through ONE copy of the trace
+  // code: the unrolled polynomial bodies are several KB of straight-line code each
+  FwRay m, ax, ay;
+#pragma unroll 1
+  for (int t = 0; t < 3; ++t) {
+    int tr;
+    const FwRay r = trace_ray_fw_po(ev, cam, t == 1 ? sx_dx : sx, t == 2 ? sy_dy : sy, r1, r2, t != 0, ray_id, tr);
+    if (t == 0) { m = r; tries = tr; }
+    else if (t == 1) ax = r;
+    else ay = r;
+  }
   const float w = m.ok ? cam.exposure : 0.f * cam.exposure;
   const size_t P = io.plane;
 #pragma unroll

@@ -96,14 +96,16 @@ LB_DEV void splat_work_item(const E &ev, const CamConsts<float> &cam, const Filt
   while (count < samples && total < max_total) {
     const int batch = min(32, min(samples - count, (int)(max_total - total)));
     int delta = 0;
+    // phase 1 (divergent): each lane reverse-traces its attempt, once per colour channel; ONE copy of the
+    // Newton code (the unrolled polynomial bodies are ~20 KB of straight-line code)
+    int pix0 = -1, pix1 = -1, pix2 = -1;
     if (lane < batch) {
       const uint32_t t = total + (uint32_t)lane;
       int fails = 0;
+#pragma unroll 1
       for (int ch = 0; ch < nchan; ++ch) {
         float lambda = 0.55f;
-        float rgbw[3] = {1.f, 1.f, 1.f};
         if (chroma) {  // lentil_filter.cpp:257-267
-          rgbw[0] = ch == 0 ? 3.f : 0.f; rgbw[1] = ch == 1 ? 3.f : 0.f; rgbw[2] = ch == 2 ? 3.f : 0.f;
           if (ch == 0) lambda = 0.35f + (1.0f - fc.abb_chromatic) * (0.55f - 0.35f);
           else if (ch == 2) lambda = 0.55f + fc.abb_chromatic * (0.85f - 0.55f);
         }
@@ -111,14 +113,27 @@ LB_DEV void splat_work_item(const E &ev, const CamConsts<float> &cam, const Filt
         ++n_attempts;
         int pixel = -1;
         if (trace_ray_bw_po(ev, cam, target, seed_base, t, lambda, sx, sy, n_its)) pixel = sensor_to_pixel(fc, sx, sy);
-        if (pixel < 0) { ++fails; continue; }
-        for (int a = 0; a < fc.n_aov; ++a) {
-          const float4 v = aov_value(aovs, s, a, i, (float)samples);
-          add_to_buffer(aovs, a, (unsigned)pixel, v, w.add_energy, depth, weight, rgbw, sample_base + i);
-        }
-        ++n_splats;
+        if (pixel < 0) ++fails;
+        else ++n_splats;
+        if (ch == 0) pix0 = pixel;
+        else if (ch == 1) pix1 = pixel;
+        else pix2 = pixel;
       }
       delta = 1 - fails;
+    }
+    __syncwarp();
+    // phase 2 (warp-converged): the AOV values of the source sample are warp-uniform, the pixel is per lane
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      if (ch >= nchan) break;
+      const int pixel = ch == 0 ? pix0 : (ch == 1 ? pix1 : pix2);
+      float rgbw[3] = {1.f, 1.f, 1.f};
+      if (chroma) { rgbw[0] = ch == 0 ? 3.f : 0.f; rgbw[1] = ch == 1 ? 3.f : 0.f; rgbw[2] = ch == 2 ? 3.f : 0.f; }
+      if (!__any_sync(0xffffffffu, pixel >= 0)) continue;
+      for (int a = 0; a < fc.n_aov; ++a) {
+        const float4 v = aov_value(aovs, s, a, i, (float)samples);
+        if (pixel >= 0) add_to_buffer(aovs, a, (unsigned)pixel, v, w.add_energy, depth, weight, rgbw, sample_base + i);
+      }
     }
     count += __reduce_add_sync(0xffffffffu, delta);
     total += (unsigned)batch;

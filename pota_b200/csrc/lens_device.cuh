@@ -254,6 +254,10 @@ struct TableEval {
     out[3] = poly_eval(L, P_OUT_DY, b);
   }
   LB_DEV T transmittance(const T b[5]) const { return poly_eval(L, P_OUT_T, b); }
+  LB_DEV void out5(const T b[5], T out[4], T &Tr) const {  // lens_evaluate: the 5 polynomials of pt_evaluate.h
+    out4(b, out);
+    Tr = transmittance(b);
+  }
   LB_DEV void out_jac(const T b[5], T K[4]) const {  // domega2_dx0
     K[0] = poly_eval(L, P_DODX_DX, b);
     K[1] = poly_eval(L, P_DODX_DY, b);

@@ -262,7 +262,9 @@ int camera_setup(lb_camera *c, const lb_camera_params *p, const lb_bokeh_image *
   const float focal_length = clamp_min_f(p->focal_length_lentil, 0.01);
   s.focus_distance = p->focus_dist;
   s.lambda = p->wavelength * 0.001;
-  c->lens_kernel = has_unrolled_kernel(p->lens_model) ? p->lens_model : -1;
+  // LB_FORCE_TABLE=1 selects the table-driven kernels even when the lens has unrolled ones (tests, A/B timing)
+  const char *force_table = getenv("LB_FORCE_TABLE");
+  c->lens_kernel = (has_unrolled_kernel(p->lens_model) && !(force_table && force_table[0] == '1')) ? p->lens_model : -1;
 
   // bokeh image -> CDF tables (lentil.h:222-228)
   free_bokeh(c);
@@ -435,6 +437,8 @@ int lb_camera_set_state(lb_camera *c, double aperture_radius, double sensor_shif
   refresh_consts(c);
   return LB_OK;
 }
+
+int lb_camera_kernel_kind(const lb_camera *c) { return (c && c->lens_kernel >= 0) ? 1 : 0; }
 
 int lb_camera_lens_work(const lb_camera *c, lb_lens_work *w) {
   if (!c || !w) return fail(LB_ERR_INVALID, "null argument");

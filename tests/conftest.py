@@ -27,3 +27,10 @@ def product_lib():
     if not os.path.exists(build.LIB):
         build.build()
     return camera.lib()
+
+
+@pytest.fixture(params=["unrolled", "table"])
+def kernel_kind(request, monkeypatch):
+    """Both evaluator kinds behind the same C ABI: per-lens unrolled kernels and the table-driven ones."""
+    monkeypatch.setenv("LB_FORCE_TABLE", "1" if request.param == "table" else "0")
+    return request.param

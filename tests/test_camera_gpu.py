@@ -65,8 +65,9 @@ def _check_parity(ref, got, min_ok_frac=0.9999, min_live=0.5):
 
 
 @pytest.mark.parametrize("lens_model,fstop,focus", [(5, 2.8, 150.0), (0, 1.4, 50.0), (40, 5.6, 500.0), (16, 0.0, 150.0), (37, 11.0, 1.0e7)])
-def test_create_rays_parity(lens_model, fstop, focus):
-    ref, got, *_ = _run_both(po_params(lens_model=lens_model, fstop=fstop, focus_dist=focus))
+def test_create_rays_parity(lens_model, fstop, focus, kernel_kind):
+    ref, got, gcam, _ = _run_both(po_params(lens_model=lens_model, fstop=fstop, focus_dist=focus))
+    assert gcam.kernel_kind == kernel_kind
     _check_parity(ref, got)
 
 
@@ -79,7 +80,7 @@ def test_create_rays_short_lens_small_sensor():
     # 16 mm stand-in: image circle smaller than a 36 mm sensor, so a 10 mm sensor is used (many vignetting retries)
     ref, got, *_ = _run_both(po_params(lens_model=28, sensor_width=10.0), n=100_000)
     _check_parity(ref, got, min_live=0.9)
-    assert (ref["tries"] > 0).mean() > 0.02
+    assert (ref["tries"] > 0).sum() > 50  # the retry path (counter RNG re-draw) is exercised
 
 
 def test_create_rays_blades():

@@ -82,9 +82,10 @@ def _check_images(ocam, gcam, aov, l1=2e-3, db=60.0):
 RGBA = ("RGBA", abi.LB_FILTER_GAUSSIAN, abi.LB_AOV_RGBA)
 
 
-def test_redistribution_parity_disc_aperture():
+def test_redistribution_parity_disc_aperture(kernel_kind):
     p = po_params(fstop=1.4, focus_dist=35.0, bidir_sample_mult=10)
     ocam, gcam = _run(p, 240, 135, 4, [RGBA])
+    assert gcam.kernel_kind == kernel_kind
     _check_stats(ocam, gcam)
     _check_images(ocam, gcam, 0)
 
