@@ -1,3 +1,5 @@
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -q --tb=short > gpurun_out/test.log 2>&1; tail -4 gpurun_out/test.log
-python bench.py > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err; tail -c 3000 gpurun_out/bench_full.json; tail -5 gpurun_out/bench_full.err
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --frame-scale 0.25 > gpurun_out/ncu_bench.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_create_rays -s 1 -c 1 -f -o gpurun_out/prof_k1 python bench.py --frame-scale 0.0625 --steps 1 --warmup 1 --skip-e2e --skip-splat --skip-cpu > gpurun_out/ncu_k1.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_filter_splat -s 1 -c 1 -f -o gpurun_out/prof_k2 python bench.py --frame-scale 0.0625 --steps 1 --warmup 1 --skip-e2e --skip-cpu > gpurun_out/ncu_k2.log 2>&1
+ls -la gpurun_out/
