@@ -612,13 +612,14 @@ struct orc_camera {
     float wdx[3] = {1, 1, 1}, wdy[3] = {1, 1, 1};
     trace_ray_fw_po(tries, input_dx_sx, sy, odxo, odxd, wdx, r1, r2, true, ray_id);
     trace_ray_fw_po(tries, sx, input_dx_sy, odyo, odyd, wdy, r1, r2, true, ray_id);
+    const float inv_step = 1.0f / step;  // AtVector::operator/(float) multiplies by the reciprocal [EXTERNAL, as oracle/shims/ai.h]
     for (int k = 0; k < 3; ++k) {
       o[0 + k] = origin[k];
       o[3 + k] = direction[k];
-      o[6 + k] = (odxo[k] - origin[k]) / step;     // dOdx
-      o[9 + k] = (odyo[k] - origin[k]) / step;     // dOdy
-      o[12 + k] = (odxd[k] - direction[k]) / step; // dDdx
-      o[15 + k] = (odyd[k] - direction[k]) / step; // dDdy
+      o[6 + k] = (odxo[k] - origin[k]) * inv_step;     // dOdx
+      o[9 + k] = (odyo[k] - origin[k]) * inv_step;     // dOdy
+      o[12 + k] = (odxd[k] - direction[k]) * inv_step; // dDdx
+      o[15 + k] = (odyd[k] - direction[k]) * inv_step; // dDdy
       o[18 + k] = weight[k] * exposure;
     }
   }

@@ -1,0 +1,156 @@
+"""ctypes binding of oracle/_ref/libref.so — the REFERENCE'S OWN sources compiled behind shims
+(oracle/ref.mk).  TEST INFRASTRUCTURE ONLY: pins the oracle and generates tests/golden/.
+
+Same calling conventions as oracle/orc.py.  Differences dictated by the reference's interface:
+filter_pixel derives the inverse sample density from the number of samples it is handed per pixel
+(lentil_filter.cpp:79-87), so samples of one pixel must be contiguous and spp must be a perfect
+square >= 9; `tries` is not observable; the forward retry RNG is the process-global xor128.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+
+import numpy as np
+
+from pota_b200 import abi
+
+from . import orc
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "_ref", "libref.so")
+_LIB = None
+
+
+def available() -> bool:
+    return os.path.exists(LIB_PATH)
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(LIB_PATH)
+        vp = C.c_void_p
+        L.ref_camera_create.argtypes = [C.POINTER(abi.CameraParams), C.POINTER(abi.BokehImage), C.POINTER(vp)]
+        L.ref_camera_destroy.argtypes = [vp]
+        L.ref_camera_get_state.argtypes = [vp, C.POINTER(abi.CameraState)]
+        L.ref_camera_set_state.argtypes = [vp, C.c_double, C.c_double]
+        L.ref_camera_create_rays.argtypes = [vp, C.c_size_t, C.c_uint64, C.POINTER(abi.RayIn), C.POINTER(abi.RayOut), C.c_int]
+        L.ref_filter_begin.argtypes = [vp, C.POINTER(abi.FrameDesc), C.c_int, C.POINTER(abi.AovDesc), C.c_int]
+        L.ref_filter_accumulate.argtypes = [vp, C.POINTER(abi.Samples), C.c_int]
+        L.ref_imager_resolve.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]
+        L.ref_filter_buffers.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(vp)]
+        L.ref_tea8.restype = C.c_uint
+        L.ref_tea8.argtypes = [C.c_uint, C.c_uint]
+        L.ref_rng.restype = C.c_float
+        L.ref_rng.argtypes = [C.POINTER(C.c_uint)]
+        L.ref_fast_sin.restype = C.c_float
+        L.ref_fast_sin.argtypes = [C.c_float]
+        L.ref_fast_cos.restype = C.c_float
+        L.ref_fast_cos.argtypes = [C.c_float]
+        L.ref_lens_ipow.restype = C.c_double
+        L.ref_lens_ipow.argtypes = [C.c_double, C.c_int]
+        L.ref_get_coc_thinlens.restype = C.c_float
+        L.ref_get_coc_thinlens.argtypes = [vp, C.c_float]
+        L.ref_lens_evaluate.restype = C.c_double
+        L.ref_lens_evaluate.argtypes = [vp, vp, vp]
+        L.ref_lens_pt_sample_aperture.argtypes = [vp, vp, vp, C.c_double]
+        L.ref_lens_lt_sample_aperture.restype = C.c_double
+        L.ref_lens_lt_sample_aperture.argtypes = [vp, vp, vp, vp, vp, C.c_double]
+        L.ref_trace_ray_bw_po.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_float, vp]
+        L.ref_bokeh_sample.argtypes = [vp, C.c_float, C.c_float, vp]
+        _LIB = L
+    return _LIB
+
+
+class RefCamera(orc.OracleCamera):
+    """struct Camera of the reference + its camera/filter/imager node callbacks."""
+
+    def __init__(self, params: abi.CameraParams, bokeh: np.ndarray | None = None):
+        self._h = C.c_void_p()
+        img, self._keep = orc.bokeh_image(bokeh)
+        rc = lib().ref_camera_create(C.byref(params), C.byref(img) if img is not None else None, C.byref(self._h))
+        if rc != 0:
+            raise RuntimeError(f"ref_camera_create failed: {rc}")
+        self.params = params
+
+    def close(self):
+        if self._h:
+            lib().ref_camera_destroy(self._h)
+            self._h = C.c_void_p()
+
+    @property
+    def state(self) -> abi.CameraState:
+        s = abi.CameraState()
+        lib().ref_camera_get_state(self._h, C.byref(s))
+        return s
+
+    def set_state(self, aperture_radius, sensor_shift):
+        lib().ref_camera_set_state(self._h, aperture_radius, sensor_shift)
+
+    def create_rays(self, sx, sy, dsx, dsy, lensx, lensy, ray_id_base: int = 0, nthreads: int = 1):
+        n = sx.shape[0]
+        ins = [np.ascontiguousarray(a, dtype=np.float32) for a in (sx, sy, dsx, dsy, lensx, lensy)]
+        rin = abi.RayIn(*[orc._ptr(a) for a in ins])
+        out = {k: np.zeros((3, n), np.float32) for k in orc.RAY_OUT_FIELDS}
+        out["tries"] = np.zeros(n, np.int32)
+        rout = abi.RayOut(*[orc._ptr(out[k]) for k in orc.RAY_OUT_FIELDS], orc._ptr(out["tries"]))
+        rc = lib().ref_camera_create_rays(self._h, n, ray_id_base, C.byref(rin), C.byref(rout), nthreads)
+        assert rc == 0, rc
+        return out
+
+    def counters(self):
+        raise NotImplementedError("the reference keeps no counters")
+
+    def filter_begin(self, xres, yres, aovs, xres_full=None, yres_full=None, region_min=(0, 0), spp=9):
+        aa = int(round(math.sqrt(spp)))
+        assert aa * aa == spp and aa >= 3, "the reference only redistributes at AA >= 3 with AA^2 samples per pixel"
+        self._frame = abi.FrameDesc(xres, yres, xres_full or xres, yres_full or yres, region_min[0], region_min[1])
+        arr = (abi.AovDesc * len(aovs))()
+        for i, (name, flt, role) in enumerate(aovs):
+            arr[i].name = name.encode()
+            arr[i].filter = flt
+            arr[i].role = role
+        self._naov = len(aovs)
+        rc = lib().ref_filter_begin(self._h, C.byref(self._frame), len(aovs), arr, aa)
+        assert rc == 0, rc
+
+    def filter_accumulate(self, px, py, rgba, pos_cs, inv_density, aov_values=None, raydir=None, transmission=None, flags=None, nthreads=1):
+        n = px.shape[0]
+        keep = [np.ascontiguousarray(px, np.int32), np.ascontiguousarray(py, np.int32), np.ascontiguousarray(rgba, np.float32), np.ascontiguousarray(pos_cs, np.float32)]
+        opt = [None if a is None else np.ascontiguousarray(a, dt) for a, dt in ((raydir, np.float32), (transmission, np.float32), (flags, np.uint32))]
+        av = (C.c_void_p * max(self._naov, 1))()
+        keep_av = []
+        for i in range(self._naov):
+            a = None if aov_values is None else aov_values[i]
+            if a is not None:
+                a = np.ascontiguousarray(a, np.float32)
+                keep_av.append(a)
+                av[i] = a.ctypes.data
+        S = abi.Samples(n, orc._ptr(keep[0]), orc._ptr(keep[1]), orc._ptr(keep[2]), orc._ptr(keep[3]), orc._ptr(opt[0]), orc._ptr(opt[1]), orc._ptr(opt[2]), av, inv_density)
+        rc = lib().ref_filter_accumulate(self._h, C.byref(S), nthreads)
+        assert rc == 0, rc
+
+    def filter_stats(self):
+        raise NotImplementedError("the reference keeps no counters")
+
+    def resolve(self, aov, x0=None, y0=None, w=None, h=None):
+        f = self._frame
+        x0 = f.region_min_x if x0 is None else x0
+        y0 = f.region_min_y if y0 is None else y0
+        w = f.xres if w is None else w
+        h = f.yres if h is None else h
+        out = np.zeros((h, w, 4), np.float32)
+        rc = lib().ref_imager_resolve(self._h, aov, x0, y0, w, h, orc._ptr(out))
+        assert rc == 0, rc
+        return out
+
+    def buffers(self, aov):
+        b, w = C.c_void_p(), C.c_void_p()
+        rc = lib().ref_filter_buffers(self._h, aov, C.byref(b), C.byref(w))
+        assert rc == 0, rc
+        f = self._frame
+        buf = np.ctypeslib.as_array(C.cast(b, C.POINTER(C.c_float)), shape=(f.yres, f.xres, 4)).copy()
+        wgt = np.ctypeslib.as_array(C.cast(w, C.POINTER(C.c_float)), shape=(f.yres, f.xres)).copy()
+        return buf, wgt

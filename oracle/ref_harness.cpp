@@ -1,0 +1,354 @@
+// ref_harness.cpp — drives the REFERENCE'S OWN SOURCES (compiled where they lie under /root/reference/src
+// behind oracle/shims/ai.h + the Eigen stand-in, see ref.mk) through the same C entry points as the
+// oracle.  TEST INFRASTRUCTURE: used to pin oracle/lentil_oracle.cpp against the reference itself and to
+// generate tests/golden/*.npz (tests/golden/make_golden.py).  Output only into oracle/_ref/.
+//
+// What is the reference here: struct Camera (src/lentil.h), camera_create_ray (src/lentil_camera.cpp),
+// filter_pixel (src/lentil_filter.cpp), driver_process_bucket (src/lentil_imager.cpp), src/lens.h,
+// src/global.h, src/imagebokeh.h — unmodified.  What is NOT: the Arnold SDK (shimmed), Eigen (shimmed), and
+// the per-lens generated bodies, which come from the build's lens pack in the generator's format
+// (oracle/_ref/gen/polynomial-optics/..., written by pota_b200.lensgen.emit).
+#include <ai.h>
+
+#include <chrono>
+#include <iostream>
+#include <regex>
+#include <thread>
+
+#include "../include/lentil_b200.h"
+// The three lens_* wrappers (lentil.h:1257-1313) sit behind `private:`; this test harness calls them
+// directly to pin the oracle's restatement of the generated bodies.  Layout is unaffected.
+#define private public
+#include "lentil.h"
+#undef private
+
+extern const AtNodeMethods *lentilMethods;         // lentil_camera.cpp:5
+extern const AtNodeMethods *LentilFilterDataMtd;   // lentil_filter.cpp:6
+extern const AtNodeMethods *LentilImagerMtd;       // lentil_imager.cpp:7
+
+struct ref_camera {
+  AtUniverse uni;
+  AtNode options, camera, filter, imager, op;
+  OperatorData opdata;
+  Camera *cam = nullptr;
+  std::vector<lb_aov_desc> aovs;
+  lb_frame_desc frame{};
+  int aa = 3;
+};
+
+namespace {
+void set_i(AtNode &n, const char *k, int v) { n.params[k].i = v; }
+void set_f(AtNode &n, const char *k, float v) { n.params[k].f = v; }
+void set_b(AtNode &n, const char *k, bool v) { n.params[k].b = v; }
+void set_s(AtNode &n, const char *k, const char *v) { n.params[k].s = v; }
+
+void apply_params(ref_camera *r, const lb_camera_params *p) {  // names: lentil_camera.cpp:19-52
+  AtNode &c = r->camera;
+  set_i(c, "camera_type", p->camera_type);
+  set_i(c, "bidir_sample_mult", p->bidir_sample_mult);
+  set_i(c, "units", p->units);
+  set_f(c, "sensor_width", p->sensor_width);
+  set_b(c, "enable_dof", p->enable_dof != 0);
+  set_f(c, "fstop", p->fstop);
+  set_f(c, "focus_dist", p->focus_dist);
+  set_i(c, "aperture_blades_lentil", p->aperture_blades_lentil);
+  set_f(c, "exp", p->exp);
+  set_i(c, "lens_model", p->lens_model);
+  set_f(c, "wavelength", p->wavelength);
+  set_f(c, "extra_sensor_shift", p->extra_sensor_shift);
+  set_f(c, "focal_length_lentil", p->focal_length_lentil);
+  set_f(c, "optical_vignetting", p->optical_vignetting);
+  set_f(c, "abb_spherical", p->abb_spherical);
+  set_f(c, "abb_distortion", p->abb_distortion);
+  set_f(c, "abb_coma", p->abb_coma);
+  set_f(c, "abb_chromatic", p->abb_chromatic);
+  set_i(c, "abb_chromatic_type", p->abb_chromatic_type);
+  set_f(c, "bokeh_circle_to_square", p->bokeh_circle_to_square);
+  set_f(c, "bokeh_anamorphic", p->bokeh_anamorphic);
+  set_b(c, "bokeh_enable_image", p->bokeh_enable_image != 0);
+  set_s(c, "bokeh_image_path", "shim://bokeh");
+  set_i(c, "vignetting_retries", p->vignetting_retries);
+  set_f(c, "bidir_add_energy", p->bidir_add_energy);
+  set_f(c, "bidir_add_energy_minimum_luminance", p->bidir_add_energy_minimum_luminance);
+  set_f(c, "bidir_add_energy_transition", p->bidir_add_energy_transition);
+  set_b(c, "enable_bidir_transmission", p->enable_bidir_transmission != 0);
+  set_b(c, "enable_skydome", p->enable_skydome != 0);
+}
+
+// what lentil_operator.cpp:25-171 leaves in OperatorData for the camera to copy (lentil.h:988-1012)
+void build_operator_aovs(ref_camera *r) {
+  r->opdata.aovs.clear();
+  for (size_t i = 0; i < r->aovs.size(); ++i) {
+    std::string out = std::string(r->aovs[i].name) + " RGBA lentil_replaced_filter shim_driver";
+    AOVData a(&r->uni, out);
+    a.original_filter = AtString(r->aovs[i].filter == LB_FILTER_CLOSEST ? "closest_filter" : "gaussian_filter");
+    a.index = (int)i;
+    r->opdata.aovs.push_back(a);
+  }
+  r->opdata.aovcount = (int)r->opdata.aovs.size();
+}
+
+void update_camera(ref_camera *r) {
+  shim_default_universe() = &r->uni;
+  AtNode &o = r->options;
+  set_i(o, "xres", r->frame.xres_without_region);
+  set_i(o, "yres", r->frame.yres_without_region);
+  // setup_filter computes xres = region_max - region_min + 1 (lentil.h:1079-1080)
+  set_i(o, "region_min_x", r->frame.region_min_x);
+  set_i(o, "region_min_y", r->frame.region_min_y);
+  set_i(o, "region_max_x", r->frame.region_min_x + r->frame.xres - 1);
+  set_i(o, "region_max_y", r->frame.region_min_y + r->frame.yres - 1);
+  set_i(o, "AA_samples", r->aa);
+  set_b(o, "enable_adaptive_sampling", false);
+  set_b(o, "ignore_dof", false);
+  set_b(o, "enable_progressive_render", false);
+  set_f(o, "meters_per_unit", 0.01f);
+  build_operator_aovs(r);
+  lentilMethods->Update(&r->uni.session, &r->camera);
+  r->cam = (Camera *)AiNodeGetLocalData(&r->camera);
+}
+}  // namespace
+
+extern "C" {
+
+int ref_camera_create(const lb_camera_params *p, const lb_bokeh_image *img, ref_camera **out) {
+  ref_camera *r = new ref_camera();
+  r->uni.options = &r->options;
+  r->uni.camera = &r->camera;
+  r->uni.nodes = {&r->options, &r->camera, &r->filter, &r->imager, &r->op};
+  r->uni.entry_counts["imager_denoiser_oidn"] = 1;  // -> filter_width 1.0 (lentil.h:1083-1088): no footprint overlap
+  for (AtNode *n : r->uni.nodes) n->universe = &r->uni;
+  r->options.name = "options"; r->options.entry.name = "options";
+  r->camera.name = "lentil_cam"; r->camera.entry.name = "lentil_camera";
+  r->filter.name = "lentil_replaced_filter"; r->filter.entry.name = "lentil_filter";
+  r->imager.name = "imager_lentil"; r->imager.entry.name = "imager_lentil";
+  r->op.name = "lentil_operator"; r->op.entry.name = "lentil_operator";
+  r->op.local_data = &r->opdata;
+  shim_default_universe() = &r->uni;
+  if (img && img->pixels) {
+    ShimTexture t;
+    t.w = img->width; t.h = img->height; t.c = img->channels;
+    t.px.assign(img->pixels, img->pixels + (size_t)t.w * t.h * t.c);
+    shim_textures()["shim://bokeh"] = t;
+  }
+  apply_params(r, p);
+  r->frame = lb_frame_desc{8, 8, 8, 8, 0, 0};
+  lb_aov_desc rgba{};
+  strcpy(rgba.name, "RGBA"); rgba.filter = LB_FILTER_GAUSSIAN; rgba.role = LB_AOV_RGBA;
+  r->aovs = {rgba};
+  lentilMethods->PluginInitialize(nullptr);
+  lentilMethods->Initialize(&r->uni.session, &r->camera);
+  const int aborts = shim_abort_count();
+  update_camera(r);
+  if (shim_abort_count() != aborts) { *out = r; return LB_ERR_IMAGE; }
+  *out = r;
+  return LB_OK;
+}
+void ref_camera_destroy(ref_camera *r) {
+  if (!r) return;
+  shim_default_universe() = &r->uni;
+  lentilMethods->Finish(&r->camera);
+  delete r;
+}
+
+int ref_camera_get_state(const ref_camera *r, lb_camera_state *s) {
+  const Camera *c = r->cam;
+  memset(s, 0, sizeof *s);
+  s->aperture_radius = c->aperture_radius; s->sensor_shift = c->sensor_shift; s->tan_fov = c->tan_fov;
+  s->focus_distance = c->focus_distance; s->lambda = c->lambda;
+  s->lens_outer_pupil_radius = c->lens_outer_pupil_radius; s->lens_inner_pupil_radius = c->lens_inner_pupil_radius;
+  s->lens_length = c->lens_length; s->lens_back_focal_length = c->lens_back_focal_length;
+  s->lens_effective_focal_length = c->lens_effective_focal_length; s->lens_aperture_pos = c->lens_aperture_pos;
+  s->lens_aperture_housing_radius = c->lens_aperture_housing_radius;
+  s->lens_inner_pupil_curvature_radius = c->lens_inner_pupil_curvature_radius;
+  s->lens_outer_pupil_curvature_radius = c->lens_outer_pupil_curvature_radius;
+  s->lens_field_of_view = c->lens_field_of_view; s->lens_fstop = c->lens_fstop;
+  s->lens_aperture_radius_at_fstop = c->lens_aperture_radius_at_fstop;
+  return LB_OK;
+}
+int ref_camera_set_state(ref_camera *r, double aperture_radius, double sensor_shift) {
+  r->cam->aperture_radius = aperture_radius;
+  r->cam->sensor_shift = sensor_shift;
+  return LB_OK;
+}
+
+// camera_create_ray per sample.  nthreads > 1 calls it concurrently on the shared Camera the way Arnold's
+// render threads do (the retry RNG is then the reference's racy process-global xor128, global.h:22-27).
+int ref_camera_create_rays(ref_camera *r, size_t n, uint64_t, const lb_ray_in *in, const lb_ray_out *out, int nthreads) {
+  shim_default_universe() = &r->uni;
+  float *dst[7] = {out->origin, out->dir, out->dOdx, out->dOdy, out->dDdx, out->dDdy, out->weight};
+  auto work = [&](size_t lo, size_t hi) {
+    for (size_t i = lo; i < hi; ++i) {
+      AtCameraInput ci{in->sx[i], in->sy[i], in->dsx[i], in->dsy[i], in->lensx[i], in->lensy[i], 0.f};
+      AtCameraOutput co;
+      lentilMethods->CreateRay(&r->camera, ci, co, 0);
+      const float v[7][3] = {{co.origin.x, co.origin.y, co.origin.z}, {co.dir.x, co.dir.y, co.dir.z}, {co.dOdx.x, co.dOdx.y, co.dOdx.z},
+                             {co.dOdy.x, co.dOdy.y, co.dOdy.z},       {co.dDdx.x, co.dDdx.y, co.dDdx.z}, {co.dDdy.x, co.dDdy.y, co.dDdy.z},
+                             {co.weight.r, co.weight.g, co.weight.b}};
+      for (int k = 0; k < 7; ++k)
+        if (dst[k]) { dst[k][i] = v[k][0]; dst[k][n + i] = v[k][1]; dst[k][2 * n + i] = v[k][2]; }
+      if (out->tries) out->tries[i] = -1;  // not observable through the reference's interface
+    }
+  };
+  if (nthreads <= 1) { work(0, n); return LB_OK; }
+  std::vector<std::thread> th;
+  for (int t = 0; t < nthreads; ++t) th.emplace_back(work, n * t / nthreads, n * (t + 1) / nthreads);
+  for (auto &t : th) t.join();
+  return LB_OK;
+}
+
+int ref_filter_begin(ref_camera *r, const lb_frame_desc *f, int n_aov, const lb_aov_desc *aovs, int aa_samples) {
+  r->frame = *f;
+  r->aovs.assign(aovs, aovs + n_aov);
+  r->aa = aa_samples;
+  update_camera(r);  // node_update -> setup_camera -> setup_lentil_aovs/setup_filter (lentil.h:211-281)
+  return r->cam->redistribution ? LB_OK : LB_ERR_STATE;
+}
+
+// filter_pixel for every run of consecutive samples that share (px, py); the reference derives the inverse
+// sample density from the number of samples it is handed (lentil_filter.cpp:79-87)
+int ref_filter_accumulate(ref_camera *r, const lb_samples *S, int nthreads) {
+  shim_default_universe() = &r->uni;
+  const size_t n = S->n;
+  std::vector<float> Z(4 * n), P(4 * n), vol(4 * n, 0.f), ign(4 * n, 0.f), zero(4 * n, 0.f);
+  for (size_t i = 0; i < n; ++i) {
+    P[4 * i] = S->pos_cs[4 * i]; P[4 * i + 1] = S->pos_cs[4 * i + 1]; P[4 * i + 2] = S->pos_cs[4 * i + 2];
+    Z[4 * i] = S->pos_cs[4 * i + 3];
+    if (S->flags) { vol[4 * i] = (S->flags[i] & LB_SAMPLE_VOLUME) ? 1.f : 0.f; ign[4 * i] = (S->flags[i] & LB_SAMPLE_IGNORE) ? 1.f : 0.f; }
+  }
+  AtAOVSampleIterator it;
+  it.aov_name = AtString("RGBA");
+  it.rgba = S->rgba;
+  it.aovs["P"] = {P.data(), 3};
+  it.aovs["Z"] = {Z.data(), 1};
+  it.aovs["volume"] = {vol.data(), 3};
+  it.aovs["lentil_bidir_ignore"] = {ign.data(), 1};
+  it.aovs["lentil_time"] = {zero.data(), 1};
+  it.aovs["lentil_raydir"] = {S->raydir ? S->raydir : zero.data(), 3};
+  it.aovs["transmission"] = {S->transmission ? S->transmission : zero.data(), 4};
+  for (size_t a = 0; a < r->aovs.size(); ++a) {
+    const float *v = (S->aov_values && S->aov_values[a]) ? S->aov_values[a] : S->rgba;
+    it.aovs[r->aovs[a].name] = {v, 4};
+  }
+  // runs of consecutive samples sharing a pixel
+  std::vector<std::pair<size_t, size_t>> runs;
+  for (size_t b = 0; b < n;) {
+    size_t e = b + 1;
+    while (e < n && S->px[e] == S->px[b] && S->py[e] == S->py[b]) ++e;
+    runs.push_back({b, e});
+    b = e;
+  }
+  auto work = [&](size_t lo, size_t hi) {
+    AtAOVSampleIterator local = it;  // per-thread cursor over the shared arrays
+    AtRGBA data_out;
+    for (size_t k = lo; k < hi; ++k) {
+      local.px = S->px[runs[k].first] + r->frame.region_min_x;  // filter_pixel subtracts region_min again (:99-100)
+      local.py = S->py[runs[k].first] + r->frame.region_min_y;
+      local.begin = runs[k].first; local.end = runs[k].second; local.cur = -1;
+      LentilFilterDataMtd->FilterPixel(&r->filter, &local, &data_out, AI_TYPE_RGBA);
+    }
+  };
+  // nthreads > 1: Arnold's bucket threads share the Camera's framebuffers without locks (lentil.h:828-829);
+  // only used for timing, never for parity
+  if (nthreads <= 1) work(0, runs.size());
+  else {
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; ++t) th.emplace_back(work, runs.size() * t / nthreads, runs.size() * (t + 1) / nthreads);
+    for (auto &t : th) t.join();
+  }
+  return r->cam->redistribution ? LB_OK : LB_ERR_STATE;
+}
+
+int ref_imager_resolve(ref_camera *r, int aov, int x0, int y0, int w, int h, float *rgba_out) {
+  shim_default_universe() = &r->uni;
+  AtOutputIterator oit;
+  oit.outs.push_back({AtString(r->aovs[aov].name), AI_TYPE_RGBA, rgba_out});
+  LentilImagerMtd->DriverProcessBucket(&r->imager, &oit, nullptr, x0, y0, w, h, 0);
+  return LB_OK;
+}
+
+int ref_filter_buffers(ref_camera *r, int aov, float **buffer, float **weight) {
+  Camera *c = r->cam;
+  if (aov < 0 || aov >= (int)c->aovs.size()) return LB_ERR_INVALID;
+  if (buffer) *buffer = &c->aovs[aov].buffer[0].r;
+  if (weight) *weight = c->filter_weight_buffer.data();
+  return LB_OK;
+}
+
+// ---- primitives, straight from the reference headers -------------------------------------------------------
+unsigned int ref_tea8(unsigned int v0, unsigned int v1) { return tea<8>(v0, v1); }
+float ref_rng(unsigned int *state) { return rng(*state); }
+void ref_xor128_seq(uint32_t *out, int n) { for (int i = 0; i < n; ++i) out[i] = xor128(); }  // continues the process-global state
+float ref_fast_sin(float x) { return fast_sin(x); }
+float ref_fast_cos(float x) { return fast_cos(x); }
+double ref_lens_ipow(double x, int e) { return lens_ipow(x, e); }
+void ref_concentric_disk_sample(double ox, double oy, int fast_trigo, double out[2]) {
+  Eigen::Vector2d d(0, 0);
+  concentric_disk_sample(ox, oy, d, fast_trigo != 0);
+  out[0] = d(0); out[1] = d(1);
+}
+void ref_sphereToCs(const double inpos[2], const double indir[2], double center, double R, double outpos[3], double outdir[3]) {
+  Eigen::Vector3d p(0, 0, 0), d(0, 0, 0);
+  sphereToCs(Eigen::Vector2d(inpos[0], inpos[1]), Eigen::Vector2d(indir[0], indir[1]), p, d, center, R);
+  for (int k = 0; k < 3; ++k) { outpos[k] = p(k); outdir[k] = d(k); }
+}
+void ref_csToSphere(const double inpos[3], const double indir[3], double center, double R, double outpos[2], double outdir[2]) {
+  Eigen::Vector2d p(0, 0), d(0, 0);
+  csToSphere(Eigen::Vector3d(inpos[0], inpos[1], inpos[2]), Eigen::Vector3d(indir[0], indir[1], indir[2]), p, d, center, R);
+  for (int k = 0; k < 2; ++k) { outpos[k] = p(k); outdir[k] = d(k); }
+}
+void ref_cylinderToCs(const double inpos[2], const double indir[2], double center, double R, int cyl_y, double outpos[3], double outdir[3]) {
+  Eigen::Vector3d p(0, 0, 0), d(0, 0, 0);
+  cylinderToCs(Eigen::Vector2d(inpos[0], inpos[1]), Eigen::Vector2d(indir[0], indir[1]), p, d, center, R, cyl_y != 0);
+  for (int k = 0; k < 3; ++k) { outpos[k] = p(k); outdir[k] = d(k); }
+}
+void ref_csToCylinder(const double inpos[3], const double indir[3], double center, double R, int cyl_y, double outpos[2], double outdir[2]) {
+  Eigen::Vector2d p(0, 0), d(0, 0);
+  csToCylinder(Eigen::Vector3d(inpos[0], inpos[1], inpos[2]), Eigen::Vector3d(indir[0], indir[1], indir[2]), p, d, center, R, cyl_y != 0);
+  for (int k = 0; k < 2; ++k) { outpos[k] = p(k); outdir[k] = d(k); }
+}
+int ref_logarithmic_values(double *out, int cap) {
+  auto v = logarithmic_values();
+  for (int i = 0; i < (int)v.size() && i < cap; ++i) out[i] = v[i];
+  return (int)v.size();
+}
+void ref_line_plane_intersection(const double o[3], const double d[3], double out[3]) {
+  Eigen::Vector3d r = line_plane_intersection(Eigen::Vector3d(o[0], o[1], o[2]), Eigen::Vector3d(d[0], d[1], d[2]));
+  for (int k = 0; k < 3; ++k) out[k] = r(k);
+}
+void ref_bokeh_sample(ref_camera *r, float r_row, float r_col, double out[2]) {
+  Eigen::Vector2d l(0, 0);
+  r->cam->image.bokehSample(r_row, r_col, l, 0.f, 0.f);
+  out[0] = l(0); out[1] = l(1);
+}
+double ref_lens_evaluate(ref_camera *r, const double in[5], double out[5]) {
+  Eigen::VectorXd i(5), o(5);
+  for (int k = 0; k < 5; ++k) { i(k) = in[k]; o(k) = out[k]; }
+  double t = r->cam->lens_evaluate(i, o);
+  for (int k = 0; k < 5; ++k) out[k] = o(k);
+  return t;
+}
+void ref_lens_pt_sample_aperture(ref_camera *r, double in[5], double out[5], double dist) {
+  Eigen::VectorXd i(5), o(5);
+  for (int k = 0; k < 5; ++k) { i(k) = in[k]; o(k) = out[k]; }
+  r->cam->lens_pt_sample_aperture(i, o, dist);
+  for (int k = 0; k < 5; ++k) { in[k] = i(k); out[k] = o(k); }
+}
+double ref_lens_lt_sample_aperture(ref_camera *r, const double scene[3], const double ap[2], double sensor[5], double out[5], double lambda_) {
+  Eigen::VectorXd s(5), o(5);
+  for (int k = 0; k < 5; ++k) { s(k) = sensor[k]; o(k) = out[k]; }
+  double t = r->cam->lens_lt_sample_aperture(Eigen::Vector3d(scene[0], scene[1], scene[2]), Eigen::Vector2d(ap[0], ap[1]), s, o, lambda_);
+  for (int k = 0; k < 5; ++k) { sensor[k] = s(k); out[k] = o(k); }
+  return t;
+}
+int ref_trace_ray_bw_po(ref_camera *r, const double target[3], int px, int py, int total_samples_taken, float lambda_in, double sensor_pos[2]) {
+  Eigen::Vector2d s(0, 0);
+  AtMatrix m;
+  AtShaderGlobals sg;
+  bool ok = r->cam->trace_ray_bw_po(Eigen::Vector3d(target[0], target[1], target[2]), s, px, py, total_samples_taken, m, AtVector(0, 0, 0), &sg, lambda_in, false);
+  sensor_pos[0] = s(0); sensor_pos[1] = s(1);
+  return ok ? 1 : 0;
+}
+float ref_get_coc_thinlens(ref_camera *r, float z) { return r->cam->get_coc_thinlens(AtVector(0.f, 0.f, z)); }
+
+}  // extern "C"

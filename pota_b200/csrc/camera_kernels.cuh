@@ -97,14 +97,15 @@ LB_DEV void camera_create_ray(const E &ev, const CamConsts<float> &cam, const Ra
   }
   const float w = m.ok ? cam.exposure : 0.f * cam.exposure;
   const size_t P = io.plane;
+  const float inv_fd = 1.0f / fd;
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     if (io.origin) io.origin[k * P + i] = m.o[k];
     if (io.dir) io.dir[k * P + i] = m.d[k];
-    if (io.dOdx) io.dOdx[k * P + i] = (ax.o[k] - m.o[k]) / fd;
-    if (io.dOdy) io.dOdy[k * P + i] = (ay.o[k] - m.o[k]) / fd;
-    if (io.dDdx) io.dDdx[k * P + i] = (ax.d[k] - m.d[k]) / fd;
-    if (io.dDdy) io.dDdy[k * P + i] = (ay.d[k] - m.d[k]) / fd;
+    if (io.dOdx) io.dOdx[k * P + i] = (ax.o[k] - m.o[k]) * inv_fd;
+    if (io.dOdy) io.dOdy[k * P + i] = (ay.o[k] - m.o[k]) * inv_fd;
+    if (io.dDdx) io.dDdx[k * P + i] = (ax.d[k] - m.d[k]) * inv_fd;
+    if (io.dDdy) io.dDdy[k * P + i] = (ay.d[k] - m.d[k]) * inv_fd;
     if (io.weight) io.weight[k * P + i] = w;
   }
   if (io.tries) io.tries[i] = tries;

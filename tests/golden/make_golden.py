@@ -1,0 +1,78 @@
+"""Generates tests/golden/*.npz from the REFERENCE'S OWN SOURCES (oracle/_ref/libref.so, built by
+`make -C oracle -f ref.mk` where /root/reference exists).  The fixtures travel with the repo, so the GPU
+box — which has no /root/reference — still checks the oracle and the CUDA path against reference output.
+
+    python tests/golden/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from oracle import orc, ref  # noqa: E402
+from pota_b200 import abi, workloads  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+IN_KEYS = ("sx", "sy", "dsx", "dsy", "lensx", "lensy")
+
+RAY_CASES = {
+    "rays_takumar50_f2.8": dict(lens_model=5, fstop=2.8, focus_dist=150.0),
+    "rays_angenieux49_f1.4_bokeh": dict(lens_model=0, fstop=1.4, focus_dist=50.0, bokeh_enable_image=1),
+    "rays_zeiss65_f5.6_blades_mm": dict(lens_model=40, fstop=5.6, focus_dist=500.0, aperture_blades_lentil=7, units=abi.LB_UNITS_MM),
+}
+FILTER_CASES = {
+    "filter_takumar50_multi_aov": (dict(lens_model=5, fstop=1.4, focus_dist=35.0, bidir_sample_mult=6, bidir_add_energy=0.5),
+                                   [("RGBA", 0, 1), ("light0", 0, 0), ("light1", 0, 0), ("N", 1, 0)], 3),
+    "filter_cooke50_bokeh_chromatic": (dict(lens_model=19, fstop=2.0, focus_dist=40.0, bidir_sample_mult=5, bokeh_enable_image=1, abb_chromatic=0.3),
+                                       [("RGBA", 0, 1)], 0),
+}
+
+
+def params(**kw):
+    return abi.CameraParams.defaults(camera_type=abi.LB_CAMERA_POLYNOMIAL_OPTICS, **kw)
+
+
+def main():
+    assert ref.available(), "build oracle/_ref first: make -C oracle -f ref.mk"
+    img = workloads.disc_bokeh_image(64)
+    n = 2048
+    for name, kw in RAY_CASES.items():
+        p = params(**kw)
+        bok = img if kw.get("bokeh_enable_image") else None
+        r, o = ref.RefCamera(p, bok), orc.OracleCamera(p, bok)
+        w = int(round((n * 16 / 9) ** 0.5))
+        ins = workloads.camera_samples(w, -(-n // w), 1, "cpu", 0, n, "linear")
+        arrs = [ins[k].numpy() for k in IN_KEYS]
+        out = r.create_rays(*arrs)
+        first_try = o.create_rays(*arrs)["tries"] == 0  # the reference's interface does not expose `tries`
+        s = r.state
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), params=np.frombuffer(bytes(p), np.uint8), first_try=first_try,
+                            aperture_radius=s.aperture_radius, sensor_shift=s.sensor_shift, tan_fov=s.tan_fov,
+                            **{k: a for k, a in zip(IN_KEYS, arrs)}, **{k: out[k] for k in orc.RAY_OUT_FIELDS})
+        print(name, "first-try rays", int(first_try.sum()), "of", n)
+    for name, (kw, aovs, n_extra) in FILTER_CASES.items():
+        p = params(**kw)
+        bok = img if kw.get("bokeh_enable_image") else None
+        r = ref.RefCamera(p, bok)
+        W, H, spp = 96, 54, 9
+        fr = workloads.highlight_frame(W, H, spp, r.state.tan_fov, "cpu", n_extra_aov=n_extra)
+        vals = [None] + [v.numpy() for v in fr["aov_values"][: len(aovs) - 1]] + [None] * max(0, len(aovs) - 1 - n_extra)
+        vals = vals[: len(aovs)]
+        r.filter_begin(W, H, aovs, spp=spp)
+        r.filter_accumulate(fr["px"].numpy(), fr["py"].numpy(), fr["rgba"].numpy(), fr["pos_cs"].numpy(), 1.0 / spp, aov_values=vals)
+        d = dict(params=np.frombuffer(bytes(p), np.uint8), W=W, H=H, spp=spp, n_extra=n_extra,
+                 aov_names=np.array([a[0] for a in aovs]), aov_filter=np.array([a[1] for a in aovs]), aov_role=np.array([a[2] for a in aovs]))
+        for a in range(len(aovs)):
+            buf, wgt = r.buffers(a)
+            d[f"buffer{a}"] = buf
+            d[f"resolved{a}"] = r.resolve(a)
+            d["weight"] = wgt
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **d)
+        print(name, "energy", float(d["buffer0"][..., :3].sum()))
+
+
+if __name__ == "__main__":
+    main()

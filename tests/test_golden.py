@@ -1,0 +1,123 @@
+"""Golden vectors generated from the reference's own sources (tests/golden/make_golden.py, oracle/_ref).
+
+CPU: the oracle must reproduce them exactly.  GPU (-m gpu): the CUDA path is compared with the same
+files, through the C ABI, at the tolerances of test_camera_gpu.py / test_filter_gpu.py.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import orc
+from pota_b200 import abi, workloads
+from tests.util import rel_err_vec
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+IN_KEYS = ("sx", "sy", "dsx", "dsy", "lensx", "lensy")
+RAY_FILES = sorted(glob.glob(os.path.join(GOLD, "rays_*.npz")))
+FILTER_FILES = sorted(glob.glob(os.path.join(GOLD, "filter_*.npz")))
+
+
+def _params(g):
+    return abi.CameraParams.from_buffer_copy(g["params"].tobytes())
+
+
+def _bokeh(p):
+    return workloads.disc_bokeh_image(64) if p.bokeh_enable_image else None
+
+
+def _frame(g, tan_fov):
+    W, H, spp, n_extra = int(g["W"]), int(g["H"]), int(g["spp"]), int(g["n_extra"])
+    aovs = [(str(n), int(f), int(r)) for n, f, r in zip(g["aov_names"], g["aov_filter"], g["aov_role"])]
+    fr = workloads.highlight_frame(W, H, spp, tan_fov, "cpu", n_extra_aov=n_extra)
+    vals = ([None] + list(fr["aov_values"][: len(aovs) - 1]) + [None] * len(aovs))[: len(aovs)]
+    return W, H, spp, aovs, fr, vals
+
+
+def test_fixtures_present():
+    assert len(RAY_FILES) >= 3 and len(FILTER_FILES) >= 2
+
+
+@pytest.mark.parametrize("path", RAY_FILES, ids=os.path.basename)
+def test_oracle_reproduces_reference_rays(path):
+    g = np.load(path)
+    p = _params(g)
+    cam = orc.OracleCamera(p, _bokeh(p))
+    s = cam.state
+    assert s.aperture_radius == float(g["aperture_radius"]) and s.sensor_shift == float(g["sensor_shift"]) and s.tan_fov == float(g["tan_fov"])
+    out = cam.create_rays(*[g[k] for k in IN_KEYS])
+    m = g["first_try"]
+    np.testing.assert_array_equal(out["tries"] == 0, m)
+    for k in orc.RAY_OUT_FIELDS:
+        np.testing.assert_array_equal(out[k][:, m], g[k][:, m], err_msg=k)
+
+
+@pytest.mark.parametrize("path", FILTER_FILES, ids=os.path.basename)
+def test_oracle_reproduces_reference_framebuffers(path):
+    g = np.load(path)
+    p = _params(g)
+    cam = orc.OracleCamera(p, _bokeh(p))
+    W, H, spp, aovs, fr, vals = _frame(g, cam.state.tan_fov)
+    cam.filter_begin(W, H, aovs)
+    cam.filter_accumulate(fr["px"].numpy(), fr["py"].numpy(), fr["rgba"].numpy(), fr["pos_cs"].numpy(), 1.0 / spp,
+                          aov_values=[None if v is None else v.numpy() for v in vals])
+    for a in range(len(aovs)):
+        buf, wgt = cam.buffers(a)
+        np.testing.assert_array_equal(buf, g[f"buffer{a}"])
+        np.testing.assert_array_equal(wgt, g["weight"])
+        np.testing.assert_array_equal(cam.resolve(a), g[f"resolved{a}"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", RAY_FILES, ids=os.path.basename)
+def test_gpu_rays_against_reference_golden(path, kernel_kind):
+    import torch
+
+    from pota_b200.camera import Camera
+
+    g = np.load(path)
+    p = _params(g)
+    cam = Camera(p, _bokeh(p), device=0)
+    s = cam.state
+    assert s.aperture_radius == float(g["aperture_radius"]) and s.sensor_shift == float(g["sensor_shift"]) and s.tan_fov == float(g["tan_fov"])
+    out = cam.create_rays(*[torch.from_numpy(g[k]).cuda() for k in IN_KEYS])
+    torch.cuda.synchronize()
+    got = {k: v.cpu().numpy() for k, v in out.items()}
+    m = g["first_try"] & (got["tries"] == 0)
+    assert m.sum() >= 0.999 * g["first_try"].sum()
+    np.testing.assert_array_equal(got["weight"][:, m], g["weight"][:, m])
+    for k in ("origin", "dir"):
+        e = rel_err_vec(got[k][:, m], g[k][:, m])
+        assert (e <= 1e-4).mean() >= 0.999, (k, e.max())
+    for k, base in (("dOdx", "origin"), ("dOdy", "origin"), ("dDdx", "dir"), ("dDdy", "dir")):
+        unit = np.spacing(np.abs(g[base][:, m]).max(axis=0).astype(np.float32)) / 1e-3
+        d = np.abs(got[k][:, m] - g[k][:, m]).max(axis=0) / unit
+        assert np.median(d) <= 1.0 and np.quantile(d, 0.99) <= 4.0, (k, np.median(d), np.quantile(d, 0.99))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", FILTER_FILES, ids=os.path.basename)
+def test_gpu_framebuffers_against_reference_golden(path, kernel_kind):
+    import torch
+
+    from pota_b200.camera import Camera
+
+    g = np.load(path)
+    p = _params(g)
+    cam = Camera(p, _bokeh(p), device=0)
+    W, H, spp, aovs, fr, vals = _frame(g, cam.state.tan_fov)
+    cam.filter_begin(W, H, aovs)
+    cam.filter_accumulate(fr["px"].cuda(), fr["py"].cuda(), fr["rgba"].cuda(), fr["pos_cs"].cuda(), 1.0 / spp,
+                          aov_values=[None if v is None else v.cuda() for v in vals])
+    torch.cuda.synchronize()
+    for a, (name, flt, role) in enumerate(aovs):
+        buf, wgt = cam.buffers(a)
+        ref_buf = g[f"buffer{a}"]
+        if flt == abi.LB_FILTER_GAUSSIAN:
+            l1 = np.abs(buf - ref_buf).sum() / np.abs(ref_buf).sum()
+            assert l1 <= 5e-3, (name, l1)  # small frame, few splats per pixel: single splats crossing a pixel edge weigh more
+            np.testing.assert_allclose(buf.sum(dtype=np.float64), ref_buf.sum(dtype=np.float64), rtol=2e-3)
+        else:
+            assert (np.abs(buf - ref_buf).max(axis=2) > 1e-6).mean() <= 1e-2, name
+    np.testing.assert_allclose(wgt.sum(dtype=np.float64), g["weight"].sum(dtype=np.float64), rtol=2e-3)

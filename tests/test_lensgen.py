@@ -1,0 +1,79 @@
+"""Lens pack integrity and the CUDA code generator, checked on the CPU: the emitted straight-line code
+(shared monomial DAG + FFMA chains) is executed as Python and compared with direct polynomial evaluation."""
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+from pota_b200.lensgen import emit, emit_cuda, pack
+from pota_b200.lensgen.fit import poly_eval
+from pota_b200.lensgen.prescriptions import LENS_DB_DIRS, LENS_IDS
+
+
+def test_pack_is_complete_and_float32_exact():
+    lenses = pack.load_pack()
+    assert [l["lens_id"] for l in lenses] == LENS_IDS and [l["db_dir"] for l in lenses] == LENS_DB_DIRS
+    for l in lenses:
+        assert set(l["polys"]) == set(pack.POLY_NAMES)
+        for name, terms in l["polys"].items():
+            assert 1 <= len(terms) <= 64
+            for c, e in terms:
+                assert float(np.float32(c)) == c and c != 0.0, (l["lens_id"], name)
+                assert len(e) == 5 and all(0 <= x <= 15 for x in e) and sum(e) <= l["max_degree"]
+        c = l["constants"]
+        assert c["lens_outer_pupil_radius"] < abs(c["lens_outer_pupil_curvature_radius"])
+        assert abs(c["lens_effective_focal_length"] - l["focal_mm"]) < 1e-3
+        assert c["lens_outer_pupil_geometry"] == "spherical"
+    # the pack spans the degree / term-count range of SURVEY.md §8d config C4
+    assert {l["max_degree"] for l in lenses} == {5, 7, 9, 11}
+    assert min(l["max_terms"] for l in lenses) == 12 and max(l["max_terms"] for l in lenses) == 64
+
+
+def _run_group(lines, b):
+    """Execute one emitted device function body (C statements) as numpy float64 Python."""
+    env = {"fmaf": lambda a, x, y: a * x + y, "b": b}
+    out = {"ap": [None] * 2, "J": [None] * 4, "out": [None] * 4, "K": [None] * 4}
+    env.update(out)
+    for ln in lines:
+        ln = ln.strip()
+        if not ln or ln.startswith("LB_DEV") or ln == "}":
+            continue
+        ln = re.sub(r"^(const )?float ", "", ln).rstrip(";")
+        ln = re.sub(r"(\d)f\b", r"\1", ln)  # 1.5f -> 1.5
+        if ln.startswith("b0 = "):
+            for k in range(5):
+                env[f"b{k}"] = b[k]
+            continue
+        exec(ln, {}, env)
+    return env
+
+
+@pytest.mark.parametrize("lens_index", [5, 28, 43])
+def test_emitted_code_matches_direct_evaluation(lens_index):
+    lens = pack.load_pack()[lens_index]
+    P = {n: [(c, tuple(e)) for c, e in t] for n, t in lens["polys"].items()}
+    rs = np.random.default_rng(lens_index)
+    X = np.stack([rs.uniform(-10, 10, 64), rs.uniform(-8, 8, 64), rs.uniform(-0.25, 0.25, 64), rs.uniform(-0.25, 0.25, 64), rs.uniform(0.4, 0.7, 64)])
+    d = lambda n, v: [(c, tuple(e)) for c, e in emit.derivative(P[n], v)]
+    polys = [P["ap_x"], P["ap_y"], d("ap_x", 2), d("ap_x", 3), d("ap_y", 2), d("ap_y", 3), P["out_x"], P["out_y"], P["out_dx"], P["out_dy"],
+             d("out_dx", 0), d("out_dx", 1), d("out_dy", 0), d("out_dy", 1)]
+    outs = ["ap[0]", "ap[1]", "J[0]", "J[1]", "J[2]", "J[3]", "out[0]", "out[1]", "out[2]", "out[3]", "K[0]", "K[1]", "K[2]", "K[3]"]
+    lines, muls, ffma = emit_cuda.emit_group("lt_all", "...", polys, outs)
+    env = _run_group(lines[1:], [X[k] for k in range(5)])
+    got = [env["ap"][0], env["ap"][1]] + env["J"] + env["out"] + env["K"]
+    for terms, g in zip(polys, got):
+        want = poly_eval(terms, X)
+        # float32-printed coefficients (%.9g round-trips float32) -> agreement to double rounding
+        np.testing.assert_allclose(g, want, rtol=1e-6, atol=1e-7)  # coefficients are printed with 9 significant digits (float32 literals)
+    assert ffma == sum(len([1 for c, e in t if sum(e) > 0]) for t in polys)
+    assert muls < 1.6 * ffma  # the DAG shares monomials across the 14 polynomials
+
+
+def test_upstream_headers_are_emitted_for_every_lens(tmp_path):
+    emit.emit_upstream(str(tmp_path))
+    for d in LENS_DB_DIRS:
+        for f in ("pt_evaluate.h", "pt_sample_aperture.h", "lt_sample_aperture.h", "lens_constants.h"):
+            p = tmp_path / "polynomial-optics" / "database" / "lenses" / d / "code" / f
+            assert p.exists() and p.read_text().startswith("case ")
