@@ -11,9 +11,11 @@
 // newton-w4.py:44) and evaluated from the lens pack tables (gen/lens_pack_data.inc) as flat
 // monomial sums with lens_ipow, term by term, exactly as the generated code would.
 //
-// Parity status: primitives (lens.h, global.h, imagebokeh.h) and the Camera-level loops are pinned
-// against the reference's own sources compiled behind shims (oracle/_ref, see oracle/Makefile and
-// tests/test_oracle_vs_ref.py); lens COEFFICIENTS are the build's own pack — "parity unpinned" at
+// Parity status: PINNED against the reference's own sources compiled behind stand-in headers
+// (oracle/ref.mk -> oracle/_ref/libref.so): tests/test_oracle_vs_ref.py asserts bit-identical results for
+// the primitives, the setup solvers, the generated bodies, camera_create_ray, trace_ray_bw_po and whole
+// filter_pixel + driver_process_bucket framebuffers; tests/golden/*.npz carry reference output to boxes
+// without /root/reference.  Lens COEFFICIENTS are the build's own pack — "parity unpinned" at
 // coefficient level, because the reference ships none.
 #include <algorithm>
 #include <cfloat>

@@ -9,59 +9,48 @@
 // counter (persistent CTAs).  The reference's loop
 //     for (count = 0; count < samples && total < 5*samples; ++count, ++total) { ...fail -> --count }
 // is sequential only through its stop rule; attempt `total` itself depends on nothing but `total`
-// (seed = tea<8>(px*py+px, total+tries)).  Each round the warp runs min(32, samples-count,
-// max_total-total) consecutive attempts, one per lane — the sequential loop is guaranteed to execute
-// at least that many more, because `count` grows by at most one per attempt — so the set of splats is
-// exactly the reference's.
+// (seed = tea<8>(px*py+px, total+tries)).  Attempt t runs iff count_before(t) = t - fails_before(t) <
+// samples, and fails_before(t) >= the failures already KNOWN among completed attempts, so every attempt
+// t < min(samples + known_fails, 5*samples) is certain to be executed by the sequential loop.  Lanes
+// therefore pull the next certain attempt as soon as their own ends ("work refill"): the set of splats
+// is exactly the reference's, and a lane never waits for a slower neighbour.
+//
+// The Newton solve is advanced ONE iteration per loop trip for all busy lanes: iteration counts differ
+// per attempt (mean ~30, up to 100), and a per-attempt inner loop left 2/3 of the lanes idle
+// (profiles/r01_k2_filter_splat_ncu.txt: 10.97 of 32 lanes active).
 #pragma once
 #include "filter_common.cuh"
 
 namespace lb {
 
-// Camera::trace_ray_bw_po, lentil.h:573-661 (AiTraceProbe occlusion test: no scene here, never occluded)
-template <typename E>
-LB_DEV bool trace_ray_bw_po(const E &ev, const CamConsts<float> &cam, const float target[3], uint32_t seed_base, uint32_t total,
-                            float lambda, float &sx, float &sy, unsigned &newton_its) {
-  int tries = 0;
-  float ax = 0.f, ay = 0.f;
-  while (tries <= cam.vignetting_retries) {
-    if (!cam.enable_dof) { ax = ay = 0.f; }
-    else {
-      uint32_t seed = tea8(seed_base, total + (uint32_t)tries);
-      if (cam.blades <= 2) {
-        float ux, uy;
-        if (cam.bokeh_n > 0) {
-          // bokehSample(rng, rng, unit_disk, rng, rng): g++ evaluates the arguments right to left, so the
-          // two unused stratification numbers draw first, then column, then row
-          lcg_rng(seed); lcg_rng(seed);
-          const float col = lcg_rng(seed);
-          const float row = lcg_rng(seed);
-          bokeh_sample(cam, row, col, ux, uy);
-        } else {
-          const float oy = lcg_rng(seed);
-          const float ox = lcg_rng(seed);
-          concentric_disk_sample(ox, oy, ux, uy);
-        }
-        ax = ux * cam.aperture_radius;
-        ay = uy * cam.aperture_radius;
-      } else {
-        const float r2 = lcg_rng(seed);
-        const float r1 = lcg_rng(seed);
-        sample_triangular_aperture(ax, ay, r1, r2, cam.aperture_radius, cam.blades);
-      }
+// lanes that must be waiting before the (divergent) service phase of the splat loop runs
+constexpr int kServiceBatch = 8;
+
+// aperture point of attempt `total`, try `tries` (lentil.h:594-609)
+LB_DEV void bw_aperture_sample(const CamConsts<float> &cam, uint32_t seed_base, uint32_t total, int tries, float &ax, float &ay) {
+  if (!cam.enable_dof) { ax = ay = 0.f; return; }
+  uint32_t seed = tea8(seed_base, total + (uint32_t)tries);
+  if (cam.blades <= 2) {
+    float ux, uy;
+    if (cam.bokeh_n > 0) {
+      // bokehSample(rng, rng, unit_disk, rng, rng): g++ evaluates the arguments right to left, so the
+      // two unused stratification numbers draw first, then column, then row
+      lcg_rng(seed); lcg_rng(seed);
+      const float col = lcg_rng(seed);
+      const float row = lcg_rng(seed);
+      bokeh_sample(cam, row, col, ux, uy);
+    } else {
+      const float oy = lcg_rng(seed);
+      const float ox = lcg_rng(seed);
+      concentric_disk_sample(ox, oy, ux, uy);
     }
-    float sensor[4], out[4];
-    int its;
-    const float T = lt_sample_aperture(ev, cam, target, ax, ay, lambda, sensor, out, &its);
-    newton_its += (unsigned)its;
-    if (T <= 0.f) { ++tries; continue; }
-    const float px = sensor[0] + sensor[2] * cam.bfl, py = sensor[1] + sensor[3] * cam.bfl;
-    if (px * px + py * py > cam.inner_pupil_r2) { ++tries; continue; }
-    sx = sensor[0] + sensor[2] * -cam.sensor_shift;  // shift sensor (lentil.h:654-655)
-    sy = sensor[1] + sensor[3] * -cam.sensor_shift;
-    return true;
+    ax = ux * cam.aperture_radius;
+    ay = uy * cam.aperture_radius;
+  } else {
+    const float r2 = lcg_rng(seed);
+    const float r1 = lcg_rng(seed);
+    sample_triangular_aperture(ax, ay, r1, r2, cam.aperture_radius, cam.blades);
   }
-  return false;
 }
 
 // sensor position -> pixel index or -1 (lentil_filter.cpp:276-290), in double like the reference
@@ -74,69 +63,132 @@ LB_DEV int sensor_to_pixel(const FilterConsts &fc, float sx, float sy) {
   return (int)floor(p0) + (int)floor(p1) * fc.xres;
 }
 
+LB_DEV float channel_lambda(const FilterConsts &fc, int ch) {  // lentil_filter.cpp:254-267
+  if (!(fc.abb_chromatic > 0.0f)) return 0.55f;
+  if (ch == 0) return 0.35f + (1.0f - fc.abb_chromatic) * (0.55f - 0.35f);
+  if (ch == 2) return 0.55f + fc.abb_chromatic * (0.85f - 0.55f);
+  return 0.55f;
+}
+
 template <typename E>
 LB_DEV void splat_work_item(const E &ev, const CamConsts<float> &cam, const FilterConsts &fc, const AovSet &aovs, const SampleIO &s,
                             const WorkItem &w, FilterCounters *counters, uint64_t sample_base) {
   const int lane = threadIdx.x & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
   const size_t i = w.sample;
   const int px = __ldg(s.px + i), py = __ldg(s.py + i);
   const float depth = __ldg(s.pos_cs + i).w;
   // -camera_space_sample_position * 10.0 (lentil_filter.cpp:271)
   const float target[3] = {(float)(-(double)w.csp[0] * 10.0), (float)(-(double)w.csp[1] * 10.0), (float)(-(double)w.csp[2] * 10.0)};
   const int samples = (int)w.n_samples;
-  const unsigned max_total = (unsigned)samples * 5u;
+  const int max_total = samples * 5;
   const float inv_samples = (float)(1.0 / (double)(float)samples);
   const float weight = 1.0f * s.inv_density * inv_samples;  // filter_weight * inverse_sample_density * inv_samples (:297)
   const uint32_t seed_base = (uint32_t)(px * py + px);
   const bool chroma = fc.abb_chromatic > 0.0f;
   const int nchan = chroma ? 3 : 1;
-  int count = 0;
-  unsigned total = 0;
+
+  // warp-uniform bookkeeping of the stop rule
+  int next = 0;         // next attempt index (`total_samples_taken`) to hand out
+  int known_fails = 0;  // channel failures among COMPLETED attempts
   unsigned n_splats = 0, n_attempts = 0, n_its = 0;
-  while (count < samples && total < max_total) {
-    const int batch = min(32, min(samples - count, (int)(max_total - total)));
-    int delta = 0;
-    // phase 1 (divergent): each lane reverse-traces its attempt, once per colour channel; ONE copy of the
-    // Newton code (the unrolled polynomial bodies are ~20 KB of straight-line code)
-    int pix0 = -1, pix1 = -1, pix2 = -1;
-    if (lane < batch) {
-      const uint32_t t = total + (uint32_t)lane;
-      int fails = 0;
-#pragma unroll 1
-      for (int ch = 0; ch < nchan; ++ch) {
-        float lambda = 0.55f;
-        if (chroma) {  // lentil_filter.cpp:257-267
-          if (ch == 0) lambda = 0.35f + (1.0f - fc.abb_chromatic) * (0.55f - 0.35f);
-          else if (ch == 2) lambda = 0.55f + fc.abb_chromatic * (0.85f - 0.55f);
+  // per-lane attempt state
+  enum { IDLE = 0, RUNNING = 1, PENDING = 2 };  // PENDING: Newton loop ended, try not yet finished
+  int state = IDLE;
+  int t = 0, ch = 0, tries = 0;
+  float ax = 0.f, ay = 0.f, lambda = 0.55f;
+  LtState<float> st;
+  lt_init(st);
+
+  for (;;) {
+    // ---- service phase: finish ended tries, hand out new attempts, splat -------------------------------
+    // It is divergent, scalar-ish code (transmittance polynomial, FP64 pixel mapping, RNG + CDF search), so it
+    // runs only when kServiceBatch lanes are waiting for it (or nothing else is left to do): its cost is
+    // shared by a batch of lanes instead of being paid by the whole warp for every single attempt.
+    const int limit = min(samples + known_fails, max_total);
+    const unsigned running = __ballot_sync(0xffffffffu, state == RUNNING);
+    const unsigned pending = __ballot_sync(0xffffffffu, state == PENDING);
+    const unsigned idle = ~(running | pending);
+    const int fillable = min(__popc(idle), max(limit - next, 0));
+    if (running == 0u && pending == 0u && fillable == 0) break;
+    if (__popc(pending) + fillable >= kServiceBatch || running == 0u) {
+      int pixel = -1;  // >= 0: this lane splats channel `splat_ch` in this service phase
+      int splat_ch = 0, new_fails = 0;
+      bool need_sample = false;
+      if (state == PENDING) {  // lentil.h:633-658 after lens_lt_sample_aperture returned
+        const float T = lt_finish(ev, cam, lambda, st);
+        bool ok = T > 0.f;
+        if (ok) {
+          const float qx = st.x + st.dx * cam.bfl, qy = st.y + st.dy * cam.bfl;
+          ok = !(qx * qx + qy * qy > cam.inner_pupil_r2);
         }
-        float sx, sy;
-        ++n_attempts;
-        int pixel = -1;
-        if (trace_ray_bw_po(ev, cam, target, seed_base, t, lambda, sx, sy, n_its)) pixel = sensor_to_pixel(fc, sx, sy);
-        if (pixel < 0) ++fails;
-        else ++n_splats;
-        if (ch == 0) pix0 = pixel;
-        else if (ch == 1) pix1 = pixel;
-        else pix2 = pixel;
+        bool channel_done = true;
+        if (ok) {
+          const float sx = st.x + st.dx * -cam.sensor_shift;  // shift sensor (lentil.h:654-655)
+          const float sy = st.y + st.dy * -cam.sensor_shift;
+          pixel = sensor_to_pixel(fc, sx, sy);
+          splat_ch = ch;
+          if (pixel < 0) new_fails = 1;  // off-image: `--count; continue` (lentil_filter.cpp:282-287)
+          else ++n_splats;
+        } else if (++tries <= cam.vignetting_retries) {  // vignetted: next try of the same attempt (lentil.h:592,634-645)
+          channel_done = false;
+        } else {
+          new_fails = 1;  // trace_ray_bw_po returned false (lentil_filter.cpp:271-274)
+        }
+        if (channel_done) {
+          if (++ch < nchan) {  // next colour channel of the same attempt: same seeds, other wavelength
+            tries = 0;
+            lambda = channel_lambda(fc, ch);
+            ++n_attempts;
+            state = RUNNING;
+            need_sample = true;
+          } else {
+            state = IDLE;
+          }
+        } else {
+          state = RUNNING;
+          need_sample = true;
+        }
       }
-      delta = 1 - fails;
-    }
-    __syncwarp();
-    // phase 2 (warp-converged): the AOV values of the source sample are warp-uniform, the pixel is per lane
-#pragma unroll
-    for (int ch = 0; ch < 3; ++ch) {
-      if (ch >= nchan) break;
-      const int pixel = ch == 0 ? pix0 : (ch == 1 ? pix1 : pix2);
-      float rgbw[3] = {1.f, 1.f, 1.f};
-      if (chroma) { rgbw[0] = ch == 0 ? 3.f : 0.f; rgbw[1] = ch == 1 ? 3.f : 0.f; rgbw[2] = ch == 2 ? 3.f : 0.f; }
-      if (!__any_sync(0xffffffffu, pixel >= 0)) continue;
-      for (int a = 0; a < fc.n_aov; ++a) {
-        const float4 v = aov_value(aovs, s, a, i, (float)samples);
-        if (pixel >= 0) add_to_buffer(aovs, a, (unsigned)pixel, v, w.add_energy, depth, weight, rgbw, sample_base + i);
+      known_fails += __reduce_add_sync(0xffffffffu, new_fails);
+      // hand the next CERTAIN attempts to idle lanes (the failures just learnt may have raised the limit)
+      {
+        const unsigned free_lanes = __ballot_sync(0xffffffffu, state == IDLE);
+        const int navail = max(min(samples + known_fails, max_total) - next, 0);
+        const int rank = __popc(free_lanes & lt_mask);
+        if (state == IDLE && rank < navail) {
+          state = RUNNING;
+          t = next + rank;
+          ch = 0;
+          tries = 0;
+          lambda = channel_lambda(fc, 0);
+          ++n_attempts;
+          need_sample = true;
+        }
+        next += min(__popc(free_lanes), navail);
+      }
+      if (need_sample) {  // the one copy of the aperture sampling code
+        bw_aperture_sample(cam, seed_base, (uint32_t)t, tries, ax, ay);
+        lt_init(st);
+      }
+      __syncwarp();
+      // splat (warp-converged): the AOV values of the source sample are warp-uniform, the pixel is per lane
+      if (__any_sync(0xffffffffu, pixel >= 0)) {
+        float rgbw[3] = {1.f, 1.f, 1.f};
+        if (chroma) { rgbw[0] = splat_ch == 0 ? 3.f : 0.f; rgbw[1] = splat_ch == 1 ? 3.f : 0.f; rgbw[2] = splat_ch == 2 ? 3.f : 0.f; }
+        for (int a = 0; a < fc.n_aov; ++a) {
+          const float4 v = aov_value(aovs, s, a, i, (float)samples);
+          if (pixel >= 0) add_to_buffer(aovs, a, (unsigned)pixel, v, w.add_energy, depth, weight, rgbw, sample_base + i);
+        }
       }
     }
-    count += __reduce_add_sync(0xffffffffu, delta);
-    total += (unsigned)batch;
+
+    // ---- one Newton iteration of lt_sample_aperture for every running lane ------------------------------
+    if (state == RUNNING) {
+      lt_iterate(ev, cam, target, ax, ay, lambda, st);
+      ++n_its;
+      if (!lt_continue(st)) state = PENDING;
+    }
   }
   n_splats = __reduce_add_sync(0xffffffffu, n_splats);
   n_attempts = __reduce_add_sync(0xffffffffu, n_attempts);

@@ -295,53 +295,81 @@ LB_DEV int pt_sample_aperture(const E &ev, T x, T y, T &dx, T &dy, T lambda, T a
 }
 
 // lt_sample_aperture: solve sensor (x,y,dx,dy) so that the ray passes aperture point (ax,ay) and
-// leaves the outer pupil towards `scene`.  Returns max(0, transmittance); iteration count in *its.
+// leaves the outer pupil towards `scene`.  The generated loop body is exposed one iteration at a time
+// (lt_init / lt_continue / lt_iterate / lt_finish) so that the splat kernel can advance all lanes of a
+// warp by one iteration per trip and refill finished lanes; lt_sample_aperture is the plain loop.
+template <typename T>
+struct LtState {
+  T x, y, dx, dy;
+  T sqr_err, sqr_ap_err;
+  T out[4];
+  int error, k;
+};
+template <typename T>
+LB_DEV void lt_init(LtState<T> &s) {
+  s.x = s.y = s.dx = s.dy = T(0);
+  s.sqr_err = s.sqr_ap_err = T(1e30);
+  s.out[0] = s.out[1] = s.out[2] = s.out[3] = T(0);
+  s.error = 0;
+  s.k = 0;
+}
+template <typename T>
+LB_DEV bool lt_continue(const LtState<T> &s) {  // for(k<100 && (sqr_err>eps || sqr_ap_err>eps) && error==0)
+  const T eps = T(1e-8);
+  return s.k < 100 && (s.sqr_err > eps || s.sqr_ap_err > eps) && s.error == 0;
+}
+template <typename T, typename E, typename C>
+LB_DEV void lt_iterate(const E &ev, const C &cam, const T scene[3], T ax, T ay, T lambda, LtState<T> &s) {
+  const T prev_sqr_err = s.sqr_err, prev_sqr_ap_err = s.sqr_ap_err;
+  const T b[5] = {s.x, s.y, s.dx, s.dy, lambda};
+  T ap[2], J[4], K[4];
+  ev.lt_all(b, ap, J, s.out, K);
+  const T da0 = ax - ap[0], da1 = ay - ap[1];
+  s.sqr_ap_err = da0 * da0 + da1 * da1;
+  const T invdetap = T(1) / (J[0] * J[3] - J[1] * J[2]);
+  s.dx += (J[3] * invdetap) * da0;
+  s.dx += (-J[1] * invdetap) * da1;
+  s.dy += (-J[2] * invdetap) * da0;
+  s.dy += (J[0] * invdetap) * da1;
+  T pos[3], dir[3];
+  outer_to_cs(cam, s.out, pos, dir);
+  const T view[3] = {scene[0] - pos[0], scene[1] - pos[1], scene[2] - pos[2]};
+  T ndx, ndy;
+  cs_to_outer(cam, pos, view, ndx, ndy);
+  const T do0 = ndx - s.out[2], do1 = ndy - s.out[3];
+  s.sqr_err = do0 * do0 + do1 * do1;
+  const T invdet = T(1) / (K[0] * K[3] - K[1] * K[2]);
+  s.x += T(0.72) * (K[3] * invdet) * do0;
+  s.x += T(0.72) * (-K[1] * invdet) * do1;
+  s.y += T(0.72) * (-K[2] * invdet) * do0;
+  s.y += T(0.72) * (K[0] * invdet) * do1;
+  int error = s.error;
+  if (s.sqr_err > prev_sqr_err) error |= 1;
+  if (s.sqr_ap_err > prev_sqr_ap_err) error |= 2;
+  if (s.out[0] != s.out[0]) error |= 4;
+  if (s.out[0] * s.out[0] + s.out[1] * s.out[1] > cam.outer_pupil_r2) error |= 16;
+  if (s.k < 10) error = 0;  // "error reset (k<10)", tests/aperture_sampling_debug/writout.txt:40
+  s.error = error;
+  s.k += 1;
+}
+// after the loop: final pupil test and transmittance; returns max(0, out[4])
+template <typename T, typename E, typename C>
+LB_DEV T lt_finish(const E &ev, const C &cam, T lambda, const LtState<T> &s) {
+  int error = s.error;
+  if (s.out[0] * s.out[0] + s.out[1] * s.out[1] > cam.outer_pupil_r2) error |= 16;
+  if (error != 0) return T(0);
+  const T b[5] = {s.x, s.y, s.dx, s.dy, lambda};
+  return t_max(T(0), ev.transmittance(b));
+}
 template <typename T, typename E, typename C>
 LB_DEV T lt_sample_aperture(const E &ev, const C &cam, const T scene[3], T ax, T ay, T lambda, T sensor[4], T out[4], int *its) {
-  T x = 0, y = 0, dx = 0, dy = 0;
-  int error = 0;
-  const T eps = T(1e-8);
-  T sqr_err = T(1e30), sqr_ap_err = T(1e30);
-  T prev_sqr_err = T(1e32), prev_sqr_ap_err = T(1e32);
-  out[0] = out[1] = out[2] = out[3] = T(0);
-  int k = 0;
-  for (; k < 100 && (sqr_err > eps || sqr_ap_err > eps) && error == 0; k++) {
-    prev_sqr_err = sqr_err;
-    prev_sqr_ap_err = sqr_ap_err;
-    const T b[5] = {x, y, dx, dy, lambda};
-    T ap[2], J[4], K[4];
-    ev.lt_all(b, ap, J, out, K);
-    const T da0 = ax - ap[0], da1 = ay - ap[1];
-    sqr_ap_err = da0 * da0 + da1 * da1;
-    const T invdetap = T(1) / (J[0] * J[3] - J[1] * J[2]);
-    dx += (J[3] * invdetap) * da0;
-    dx += (-J[1] * invdetap) * da1;
-    dy += (-J[2] * invdetap) * da0;
-    dy += (J[0] * invdetap) * da1;
-    T pos[3], dir[3];
-    outer_to_cs(cam, out, pos, dir);
-    const T view[3] = {scene[0] - pos[0], scene[1] - pos[1], scene[2] - pos[2]};
-    T ndx, ndy;
-    cs_to_outer(cam, pos, view, ndx, ndy);
-    const T do0 = ndx - out[2], do1 = ndy - out[3];
-    sqr_err = do0 * do0 + do1 * do1;
-    const T invdet = T(1) / (K[0] * K[3] - K[1] * K[2]);
-    x += T(0.72) * (K[3] * invdet) * do0;
-    x += T(0.72) * (-K[1] * invdet) * do1;
-    y += T(0.72) * (-K[2] * invdet) * do0;
-    y += T(0.72) * (K[0] * invdet) * do1;
-    if (sqr_err > prev_sqr_err) error |= 1;
-    if (sqr_ap_err > prev_sqr_ap_err) error |= 2;
-    if (out[0] != out[0]) error |= 4;
-    if (out[0] * out[0] + out[1] * out[1] > cam.outer_pupil_r2) error |= 16;
-    if (k < 10) error = 0;
-  }
-  if (out[0] * out[0] + out[1] * out[1] > cam.outer_pupil_r2) error |= 16;
-  if (its) *its = k;
-  sensor[0] = x; sensor[1] = y; sensor[2] = dx; sensor[3] = dy;
-  if (error != 0) return T(0);
-  const T b[5] = {x, y, dx, dy, lambda};
-  return t_max(T(0), ev.transmittance(b));
+  LtState<T> s;
+  lt_init(s);
+  while (lt_continue(s)) lt_iterate(ev, cam, scene, ax, ay, lambda, s);
+  if (its) *its = s.k;
+  sensor[0] = s.x; sensor[1] = s.y; sensor[2] = s.dx; sensor[3] = s.dy;
+  out[0] = s.out[0]; out[1] = s.out[1]; out[2] = s.out[2]; out[3] = s.out[3];
+  return lt_finish(ev, cam, lambda, s);
 }
 
 }  // namespace lb
