@@ -1,0 +1,92 @@
+"""Config C5 (BASELINE.json configs[4]): 7680x4320 multi-AOV redistribution (beauty + 8 per-light RGBA AOVs + a
+closest-filter AOV), source samples partitioned by range over the ranks, NCCL framebuffer reduce, resolve on rank 0.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29513 scripts/run_c5.py [--spp 16]
+    python scripts/run_c5.py --spp 4          (single GPU)
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from pota_b200 import abi, workloads  # noqa: E402
+from pota_b200.camera import Camera  # noqa: E402
+
+W, H = 7680, 4320
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--spp", type=int, default=16)
+    ap.add_argument("--steps", type=int, default=2)
+    a = ap.parse_args()
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    p = abi.CameraParams.defaults(camera_type=1, lens_model=5, fstop=1.4, focus_dist=35.0, bidir_sample_mult=10, bokeh_enable_image=1)
+    cam = Camera(p, bokeh=workloads.disc_bokeh_image(250), device=local)
+    aovs = [("RGBA", 0, 1)] + [(f"light{k}", 0, 0) for k in range(8)] + [("N", 1, 0)]
+    total = W * H * a.spp
+    lo, hi = total * rank // world, total * (rank + 1) // world
+    cam.filter_begin(W, H, aovs)
+    if world > 1:
+        uid = [Camera.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        cam.comm_init(world, rank, uid[0])
+    chunk = 1920 * 1080 * 16  # source samples generated and accumulated per call
+    stream = torch.cuda.current_stream()
+    times = []
+    for step in range(a.steps + 1):
+        cam.filter_begin(W, H, aovs)
+        cam.filter_set_sample_base(lo)
+        t_acc = t_red = 0.0
+        for c0 in range(lo, hi, chunk):
+            m = min(chunk, hi - c0)
+            fr = workloads.highlight_frame(W, H, a.spp, cam.state.tan_fov, dev, c0, m, grid=(8, 4), n_extra_aov=8)
+            vals = [None] + fr["aov_values"] + [fr["aov_values"][0]]
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            cam.filter_accumulate(fr["px"], fr["py"], fr["rgba"], fr["pos_cs"], 1.0 / a.spp, aov_values=vals, stream=stream)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            t_acc += e0.elapsed_time(e1)
+            del fr, vals
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        if world > 1:
+            dist.barrier()
+        e0.record(stream)
+        cam.filter_reduce(root=0, stream=stream)
+        e1.record(stream)
+        imgs = [cam.resolve(k, stream=stream) for k in range(len(aovs))] if rank == 0 else []
+        e2.record(stream)
+        torch.cuda.synchronize()
+        t_red, t_res = e0.elapsed_time(e1), e1.elapsed_time(e2)
+        st = cam.filter_stats()
+        if step > 0:
+            times.append((t_acc, t_red, t_res, st["splats"]))
+        del imgs
+    t = torch.tensor([[x[0], x[1], x[2], x[3]] for x in times], dtype=torch.float64, device=dev).mean(0)
+    tmax = t.clone()
+    tsum = t.clone()
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        splats = float(tsum[3])
+        total_ms = float(tmax[0] + tmax[1] + tmax[2])
+        block_gb = W * H * (4 * len(aovs) + 1) * 4 / 1e9
+        print(json.dumps({"config": f"C5 {W}x{H}x{a.spp}spp, {len(aovs)} AOVs (9 gaussian RGBA + 1 closest), {world} GPU(s)", "accumulate_ms": float(tmax[0]),
+                          "reduce_ms": float(tmax[1]), "resolve_ms": float(tmax[2]), "splats": splats, "splats_per_s": splats / (total_ms * 1e-3),
+                          "framebuffer_block_GB": block_gb, "reduce_GBps_per_rank": block_gb / (float(tmax[1]) * 1e-3) if world > 1 else None}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

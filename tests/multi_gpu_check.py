@@ -1,0 +1,69 @@
+"""Multi-GPU check of lb_filter_reduce, run under torchrun on a box with >= 2 GPUs (not collected by pytest):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/multi_gpu_check.py
+
+Every rank accumulates its sample range of one frame; after the NCCL combine rank 0 must hold the same
+framebuffers (gaussian AOVs, weight, closest AOV) as a single-GPU run over all samples.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from pota_b200 import abi, workloads  # noqa: E402
+from pota_b200.camera import Camera  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    p = abi.CameraParams.defaults(camera_type=1, lens_model=5, fstop=1.4, focus_dist=35.0, bidir_sample_mult=6)
+    W, H, spp = 320, 180, 4
+    aovs = [("RGBA", 0, 1), ("light0", 0, 0), ("N", 1, 0)]
+    total = W * H * spp
+
+    def run(cam, lo, hi, dev):
+        fr = workloads.highlight_frame(W, H, spp, cam.state.tan_fov, dev, lo, hi - lo, n_extra_aov=2)
+        cam.filter_begin(W, H, aovs)
+        cam.filter_set_sample_base(lo)
+        cam.filter_accumulate(fr["px"], fr["py"], fr["rgba"], fr["pos_cs"], 1.0 / spp, aov_values=[None, fr["aov_values"][0], fr["aov_values"][1]])
+        return fr
+
+    dev = torch.device("cuda", local)
+    cam = Camera(p, device=local)
+    lo, hi = total * rank // world, total * (rank + 1) // world
+    keep = run(cam, lo, hi, dev)
+    uid = [Camera.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    cam.comm_init(world, rank, uid[0])
+    for root in (0, -1):  # reduce to rank 0, then all-reduce on fresh partials
+        if root == -1:
+            keep = run(cam, lo, hi, dev)
+        cam.filter_reduce(root=root)
+        torch.cuda.synchronize()
+        if rank == 0 or root == -1:
+            single = Camera(p, device=local)
+            keep2 = run(single, 0, total, dev)
+            torch.cuda.synchronize()
+            for a, (name, flt, role) in enumerate(aovs):
+                got, gw = cam.buffers(a)
+                ref, rw = single.buffers(a)
+                if flt == 0:
+                    np.testing.assert_allclose(got, ref, rtol=2e-5, atol=2e-5, err_msg=f"root={root} {name}")
+                    np.testing.assert_allclose(gw, rw, rtol=2e-5, atol=1e-6)
+                else:
+                    assert (np.abs(got - ref).max(axis=2) > 1e-6).mean() < 1e-3, f"root={root} closest {name}"
+            assert cam.filter_stats()["splats"] > 0
+    dist.barrier()
+    cam.comm_destroy()
+    if rank == 0:
+        print(f"multi_gpu_check ok: world={world}, {total} samples, reduce + all-reduce match the single-GPU framebuffers")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

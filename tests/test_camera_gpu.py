@@ -131,3 +131,33 @@ def test_reverse_rays():
     t = cam.state.tan_fov
     exp = np.array([[1.0 / (10.0 * t), 2.0 / (10.0 * t)], [0.5 / 1e-3, -0.25 / 1e-3]], np.float32)
     np.testing.assert_allclose(Ps, exp, rtol=1e-6)
+
+
+@pytest.mark.parametrize("lens_model", range(44))
+def test_every_lens_of_the_pack(lens_model):
+    """Config C4: all 44 LensModel ids (polynomial degree 5..11, 12..64 terms), unrolled kernels, rays + a small splat frame."""
+    from oracle import orc
+    from pota_b200.camera import Camera
+
+    name = Camera.__module__ and __import__("pota_b200.camera", fromlist=["lens_names"]).lens_names()[lens_model]
+    focal = float(name.split("__")[-1].replace("mm", ""))
+    sensor = min(36.0, 0.7 * focal)  # the short stand-ins do not cover a 36 mm sensor
+    p = po_params(lens_model=lens_model, fstop=2.0, focus_dist=100.0, sensor_width=sensor, bidir_sample_mult=8)
+    ref, got, gcam, _ = _run_both(p, n=20_000)
+    assert gcam.kernel_kind == "unrolled"
+    _check_parity(ref, got, min_ok_frac=0.999, min_live=0.8)
+    # reverse path on the same lens
+    ocam = orc.OracleCamera(p)
+    W, H, spp = 96, 54, 4
+    fr = workloads.highlight_frame(W, H, spp, ocam.state.tan_fov, "cpu", z_plane=40.0, pitch=4.0, radius=0.2)
+    aovs = [("RGBA", abi.LB_FILTER_GAUSSIAN, abi.LB_AOV_RGBA)]
+    ocam.filter_begin(W, H, aovs)
+    ocam.filter_accumulate(fr["px"].numpy(), fr["py"].numpy(), fr["rgba"].numpy(), fr["pos_cs"].numpy(), 1.0 / spp, nthreads=8)
+    gcam.filter_begin(W, H, aovs)
+    gcam.filter_accumulate(fr["px"].cuda(), fr["py"].cuda(), fr["rgba"].cuda(), fr["pos_cs"].cuda(), 1.0 / spp)
+    so, sg = ocam.filter_stats(), gcam.filter_stats()
+    assert so["redistributed"] == sg["redistributed"] and so["redistributed"] > 0, (so, sg)
+    assert abs(so["splats"] - sg["splats"]) <= 5e-3 * so["splats"] + 3, (so, sg)
+    bo, _ = ocam.buffers(0)
+    bg, _ = gcam.buffers(0)
+    assert np.abs(bg - bo).sum() / np.abs(bo).sum() <= 1e-2
