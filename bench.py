@@ -51,30 +51,69 @@ def splat_params():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons every 200 ms while the timed region runs."""
+    """SM clock + throttle reasons sampled every 20 ms through NVML while the timed region runs
+    (nvidia-smi -lms as the fallback: its start-up alone can outlast a sub-second timed region)."""
 
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index: int):
         self.index = index
-        self.rows = []
+        self.sm, self.reasons, self.max_mhz = [], set(), None
         self.proc = None
+        self._stop = threading.Event()
+        self._nvml = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nvml = None
+
+    def _poll_nvml(self):
+        n = self._nvml
+        bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM)))
+                r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for name, bit in bits.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def _read_smi(self):
+        for line in self.proc.stdout:
+            c = [x.strip() for x in line.split(",")]
+            try:
+                self.sm.append(float(c[0]))
+                self.max_mhz = max(self.max_mhz or 0.0, float(c[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[3:7]):
+                if v.lower().startswith("active"):
+                    self.reasons.add(name)
 
     def __enter__(self):
+        if self._nvml is not None:
+            self.t = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.t.start()
+            return self
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.index)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t = threading.Thread(target=self._read_smi, daemon=True)
             self.t.start()
         except OSError:
             self.proc = None
         return self
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
     def __exit__(self, *a):
+        self._stop.set()
         if self.proc:
             self.proc.terminate()
             try:
@@ -83,19 +122,10 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                mx.append(float(r[1]))
-            except (ValueError, IndexError):
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.sm),
+                "source": "nvml" if self._nvml is not None else "nvidia-smi"}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -364,7 +394,22 @@ def bench_splat(args, rank, world, local_rank, dev, barrier, max_over_ranks, sum
     its = sum_over_ranks(float(st["newton_its"]))
     w = cam.lens_work
     flop = its * (w.F_apxy + w.F_apJ + w.F_out4 + w.F_outJ + 120.0) + attempts * w.F_T
-    return {"metric": "redistributed_splats_per_s", "value": splats / s, "unit": "splats/s", "ms_per_step": s * 1e3, "scaling": "strong",
+    import ctypes
+
+    from pota_b200.camera import lib
+
+    fp32_peak, red_peak = ctypes.c_double(), ctypes.c_double()
+    lib().lb_bench_fp32_peak(local_rank, ctypes.byref(fp32_peak))
+    lib().lb_bench_red_peak(local_rank, 41, ctypes.byref(red_peak))  # 33 MB RGBA plane + 8 MB weight plane, L2-resident
+    # two rooflines: the reverse Newton trace is FP32 bound, the accumulate is reduction (L2 atomic) bound
+    passthrough = sum_over_ranks(float(st["passthrough"]))
+    red_bytes = (splats + passthrough) * 20.0  # 16 B vector reduction + 4 B weight reduction per add and gaussian RGBA AOV
+    roof = {"trace": {"bound": "fp32", "achieved": flop / s / 1e12 / world, "peak": fp32_peak.value, "unit": "TFLOP/s per GPU",
+                      "frac": flop / s / 1e12 / world / max(fp32_peak.value, 1e-9)},
+            "accumulate": {"bound": "l2_reduction", "achieved": red_bytes / s / 1e9 / world, "peak": red_peak.value, "unit": "GB/s per GPU",
+                           "frac": red_bytes / s / 1e9 / world / max(red_peak.value, 1e-9),
+                           "peak_source": "lb_bench_red_peak: red.global.add.v4.f32 at random pixels of a 41 MB plane"}}
+    return {"roofline": roof, "metric": "redistributed_splats_per_s", "value": splats / s, "unit": "splats/s", "ms_per_step": s * 1e3, "scaling": "strong",
             "config": {"workload": f"bidirectional redistribution {SPLAT_W}x{SPLAT_H}x{spp}spp synthetic highlight frame, 250x250 image-bokeh kernel, "
                                    f"{SPLAT_GRID[0]}x{SPLAT_GRID[1]} emissive discs at z=-75, f/1.4 focus 35, bidir_sample_mult 10, 1 RGBA AOV"},
             "splats_per_step": splats, "attempts_per_step": attempts, "newton_its_per_attempt": its / max(attempts, 1.0),

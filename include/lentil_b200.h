@@ -142,6 +142,9 @@ LB_API void lb_camera_destroy(lb_camera *cam); /* node_finish, lentil_camera.cpp
 LB_API int lb_camera_get_state(const lb_camera *cam, lb_camera_state *out);
 /* Override the two solver results (tests / callers that cache them). */
 LB_API int lb_camera_set_state(lb_camera *cam, double aperture_radius, double sensor_shift);
+/* Override lens_outer/inner_pupil_geometry (0 spherical, 1 cyl-y, 2 cyl-x; lentil.h:119-120): the pack's
+ * stand-in lenses are all spherical, anamorphic lenses of a user pack select the cylinder transforms. */
+LB_API int lb_camera_set_pupil_geometry(lb_camera *cam, int outer_geometry, int inner_geometry);
 
 /* camera_create_ray for n samples.  Retries after a vignetted main ray draw their lens sample
  * from the reference's own counter RNG, seed = tea<8>(ray_id_base + i, try) (global.h:32-57),
@@ -172,6 +175,9 @@ LB_API int lb_camera_lens_work(const lb_camera *cam, lb_lens_work *out);
 LB_API int lb_camera_kernel_kind(const lb_camera *cam);
 /* On-box FP32 FMA throughput in TFLOP/s (register-operand FFMA chains): roofline denominator. */
 LB_API int lb_bench_fp32_peak(int device, double *tflops_out);
+/* On-box throughput of 16-byte vector reductions (red.global.add.v4.f32) at random pixels of a `megabytes` MB
+ * plane, in GB/s: roofline denominator of the splat accumulate. */
+LB_API int lb_bench_red_peak(int device, int megabytes, double *gbytes_per_s_out);
 
 /* ---- filter / imager ---------------------------------------------------------------------- */
 

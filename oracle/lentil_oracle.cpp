@@ -988,6 +988,12 @@ int orc_camera_get_state(const orc_camera *c, lb_camera_state *s) {
   s->focus_check_distance = c->focus_check_distance;
   return LB_OK;
 }
+int orc_camera_set_pupil_geometry(orc_camera *c, int outer, int inner) {
+  if (!c) return LB_ERR_INVALID;
+  c->lens_outer_pupil_geometry = outer;
+  c->lens_inner_pupil_geometry = inner;
+  return LB_OK;
+}
 int orc_camera_set_state(orc_camera *c, double aperture_radius, double sensor_shift) {
   if (!c) return LB_ERR_INVALID;
   c->aperture_radius = aperture_radius;

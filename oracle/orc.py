@@ -32,6 +32,7 @@ def lib():
         L.orc_camera_destroy.argtypes = [C.c_void_p]
         L.orc_camera_get_state.argtypes = [C.c_void_p, C.POINTER(abi.CameraState)]
         L.orc_camera_set_state.argtypes = [C.c_void_p, C.c_double, C.c_double]
+        L.orc_camera_set_pupil_geometry.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.orc_camera_create_rays.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64, C.POINTER(abi.RayIn), C.POINTER(abi.RayOut), C.c_int]
         L.orc_filter_begin.argtypes = [C.c_void_p, C.POINTER(abi.FrameDesc), C.c_int, C.POINTER(abi.AovDesc)]
         L.orc_filter_accumulate.argtypes = [C.c_void_p, C.POINTER(abi.Samples), C.c_int]
@@ -106,6 +107,9 @@ class OracleCamera:
 
     def set_state(self, aperture_radius: float, sensor_shift: float):
         lib().orc_camera_set_state(self._h, aperture_radius, sensor_shift)
+
+    def set_pupil_geometry(self, outer: int, inner: int = 0):
+        lib().orc_camera_set_pupil_geometry(self._h, outer, inner)
 
     def create_rays(self, sx, sy, dsx, dsy, lensx, lensy, ray_id_base: int = 0, nthreads: int = 1):
         n = sx.shape[0]

@@ -36,6 +36,7 @@ def lib():
         L.ref_camera_destroy.argtypes = [vp]
         L.ref_camera_get_state.argtypes = [vp, C.POINTER(abi.CameraState)]
         L.ref_camera_set_state.argtypes = [vp, C.c_double, C.c_double]
+        L.ref_camera_set_pupil_geometry.argtypes = [vp, C.c_int, C.c_int]
         L.ref_camera_create_rays.argtypes = [vp, C.c_size_t, C.c_uint64, C.POINTER(abi.RayIn), C.POINTER(abi.RayOut), C.c_int]
         L.ref_filter_begin.argtypes = [vp, C.POINTER(abi.FrameDesc), C.c_int, C.POINTER(abi.AovDesc), C.c_int]
         L.ref_filter_accumulate.argtypes = [vp, C.POINTER(abi.Samples), C.c_int]
@@ -88,6 +89,9 @@ class RefCamera(orc.OracleCamera):
 
     def set_state(self, aperture_radius, sensor_shift):
         lib().ref_camera_set_state(self._h, aperture_radius, sensor_shift)
+
+    def set_pupil_geometry(self, outer: int, inner: int = 0):
+        lib().ref_camera_set_pupil_geometry(self._h, outer, inner)
 
     def create_rays(self, sx, sy, dsx, dsy, lensx, lensy, ray_id_base: int = 0, nthreads: int = 1):
         n = sx.shape[0]

@@ -166,6 +166,12 @@ int ref_camera_get_state(const ref_camera *r, lb_camera_state *s) {
   s->lens_aperture_radius_at_fstop = c->lens_aperture_radius_at_fstop;
   return LB_OK;
 }
+int ref_camera_set_pupil_geometry(ref_camera *r, int outer, int inner) {
+  const char *names[3] = {"spherical", "cyl-y", "cyl-x"};
+  r->cam->lens_outer_pupil_geometry = names[outer];
+  r->cam->lens_inner_pupil_geometry = names[inner];
+  return LB_OK;
+}
 int ref_camera_set_state(ref_camera *r, double aperture_radius, double sensor_shift) {
   r->cam->aperture_radius = aperture_radius;
   r->cam->sensor_shift = sensor_shift;

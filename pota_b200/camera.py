@@ -29,7 +29,7 @@ EXPORTS = [
     "lb_camera_create_rays", "lb_camera_create_rays_host", "lb_camera_reverse_rays", "lb_camera_lens_work",
     "lb_filter_begin", "lb_filter_accumulate", "lb_filter_accumulate_host", "lb_filter_get_stats",
     "lb_filter_newton_iterations", "lb_imager_resolve", "lb_imager_resolve_host", "lb_filter_buffers", "lb_filter_buffers_host",
-    "lb_bench_fp32_peak", "lb_camera_kernel_kind", "lb_comm_unique_id", "lb_comm_init", "lb_filter_set_sample_base", "lb_filter_reduce", "lb_comm_destroy",
+    "lb_bench_fp32_peak", "lb_bench_red_peak", "lb_camera_set_pupil_geometry", "lb_camera_kernel_kind", "lb_comm_unique_id", "lb_comm_init", "lb_filter_set_sample_base", "lb_filter_reduce", "lb_comm_destroy",
 ]  # fmt: skip
 
 
@@ -71,6 +71,8 @@ def lib():
         L.lb_filter_buffers_host.argtypes = [vp, i, vp, vp]
         L.lb_bench_fp32_peak.argtypes = [i, C.POINTER(C.c_double)]
         L.lb_camera_kernel_kind.argtypes = [vp]
+        L.lb_bench_red_peak.argtypes = [i, i, C.POINTER(C.c_double)]
+        L.lb_camera_set_pupil_geometry.argtypes = [vp, i, i]
         L.lb_comm_unique_id.argtypes = [C.c_char_p]
         L.lb_comm_init.argtypes = [vp, i, i, C.c_char_p]
         L.lb_filter_set_sample_base.argtypes = [vp, u64]
@@ -147,6 +149,9 @@ class Camera:
 
     def set_state(self, aperture_radius: float, sensor_shift: float):
         _check(lib().lb_camera_set_state(self._h, aperture_radius, sensor_shift))
+
+    def set_pupil_geometry(self, outer: int, inner: int = 0):
+        _check(lib().lb_camera_set_pupil_geometry(self._h, outer, inner))
 
     @property
     def kernel_kind(self) -> str:

@@ -438,6 +438,14 @@ int lb_camera_set_state(lb_camera *c, double aperture_radius, double sensor_shif
   return LB_OK;
 }
 
+int lb_camera_set_pupil_geometry(lb_camera *c, int outer_geometry, int inner_geometry) {
+  if (!c || outer_geometry < 0 || outer_geometry > 2 || inner_geometry < 0 || inner_geometry > 2) return fail(LB_ERR_INVALID, "geometry must be 0, 1 or 2");
+  c->st.outer_pupil_geometry = outer_geometry;
+  c->st.inner_pupil_geometry = inner_geometry;
+  refresh_consts(c);
+  return LB_OK;
+}
+
 int lb_camera_kernel_kind(const lb_camera *c) { return (c && c->lens_kernel >= 0) ? 1 : 0; }
 
 int lb_camera_lens_work(const lb_camera *c, lb_lens_work *w) {

@@ -58,3 +58,52 @@ extern "C" int lb_bench_fp32_peak(int device, double *tflops_out) {
   *tflops_out = best;
   return cudaGetLastError() == cudaSuccess ? LB_OK : LB_ERR_CUDA;
 }
+
+// ---- reduction throughput: red.global.add.v4.f32 into an L2-resident plane at pseudo-random pixels --------
+namespace {
+__global__ void __launch_bounds__(256) k_red_peak(float4 *buf, unsigned npx, int iters) {
+  unsigned s = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
+  const float4 v = make_float4(1.f, 1.f, 1.f, 1.f);
+  for (int i = 0; i < iters; ++i) {
+    s = s * 1664525u + 1013904223u;
+    atomicAdd(buf + (s >> 8) % npx, v);
+  }
+}
+}  // namespace
+
+// GB/s of 16-byte vector reductions (the splat accumulate of one gaussian AOV) into a `megabytes` MB plane.
+extern "C" int lb_bench_red_peak(int device, int megabytes, double *gbytes_per_s_out) {
+  if (!gbytes_per_s_out || megabytes <= 0) return LB_ERR_INVALID;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device >= ndev) return LB_ERR_NO_DEVICE;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  cudaSetDevice(device);
+  int sms = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  const unsigned npx = (unsigned)((size_t)megabytes * 1000000 / 16);
+  float4 *d = nullptr;
+  if (cudaMalloc(&d, (size_t)npx * 16) != cudaSuccess) { cudaSetDevice(prev); return LB_ERR_CUDA; }
+  cudaMemset(d, 0, (size_t)npx * 16);
+  const int grid = sms * 8, block = 256, iters = 256;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(e0);
+    k_red_peak<<<grid, block>>>(d, npx, iters);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double gbs = 16.0 * grid * block * (double)iters / (ms * 1e-3) / 1e9;
+    if (rep > 0 && gbs > best) best = gbs;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  cudaSetDevice(prev);
+  *gbytes_per_s_out = best;
+  return cudaGetLastError() == cudaSuccess ? LB_OK : LB_ERR_CUDA;
+}

@@ -1,4 +1,4 @@
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -q --tb=short -k "every_lens" > gpurun_out/test.log 2>&1; tail -4 gpurun_out/test.log
-python scripts/sweep_lenses.py > gpurun_out/sweep.txt 2>&1; tail -48 gpurun_out/sweep.txt
-python scripts/run_c5.py --spp 4 --steps 1 2>&1 | tail -3
+python -m pytest tests -m gpu -q --tb=short -x > gpurun_out/test.log 2>&1; tail -5 gpurun_out/test.log
+python bench.py > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err; python -c "
+import json; d=json.load(open('gpurun_out/bench_full.json')); print('rays/s %.3e e2e %.3e clocks %s cpu %s'%(d['value'], d['e2e']['value'], d['clocks'], d['cpu_baseline']['value'])); print(json.dumps(d['splat']['roofline'])); print(d['splat']['value'])"; tail -3 gpurun_out/bench_full.err

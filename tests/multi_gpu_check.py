@@ -57,7 +57,7 @@ def main():
                     np.testing.assert_allclose(gw, rw, rtol=2e-5, atol=1e-6)
                 else:
                     assert (np.abs(got - ref).max(axis=2) > 1e-6).mean() < 1e-3, f"root={root} closest {name}"
-            assert cam.filter_stats()["splats"] > 0
+            assert cam.filter_stats()["samples"] == hi - lo  # (a rank whose slice holds no highlight has 0 splats)
     dist.barrier()
     cam.comm_destroy()
     if rank == 0:

@@ -161,3 +161,20 @@ def test_every_lens_of_the_pack(lens_model):
     bo, _ = ocam.buffers(0)
     bg, _ = gcam.buffers(0)
     assert np.abs(bg - bo).sum() / np.abs(bo).sum() <= 1e-2
+
+
+@pytest.mark.parametrize("outer", [1, 2])
+def test_cylindrical_outer_pupil_gpu(outer, kernel_kind):
+    from oracle import orc
+    from pota_b200.camera import Camera
+
+    p = po_params(fstop=2.0, focus_dist=80.0)
+    ocam, gcam = orc.OracleCamera(p), Camera(p, device=0)
+    ocam.set_pupil_geometry(outer)
+    gcam.set_pupil_geometry(outer)
+    n = 50_000
+    ins = workloads.camera_samples(300, 170, 1, "cpu", 0, n, "linear")
+    ref = ocam.create_rays(*[ins[k].numpy() for k in ("sx", "sy", "dsx", "dsy", "lensx", "lensy")], nthreads=8)
+    out = gcam.create_rays(*[ins[k].cuda() for k in ("sx", "sy", "dsx", "dsy", "lensx", "lensy")])
+    torch.cuda.synchronize()
+    _check_parity(ref, {k: v.cpu().numpy() for k, v in out.items()}, min_ok_frac=0.999)

@@ -211,3 +211,29 @@ def test_filter_region(libs):
     r.filter_accumulate(*args)
     np.testing.assert_array_equal(o.buffers(0)[0], r.buffers(0)[0])
     np.testing.assert_array_equal(o.resolve(0), r.resolve(0))
+
+
+@pytest.mark.parametrize("outer", [1, 2])
+def test_cylindrical_outer_pupil(outer):
+    """Anamorphic lenses (lens_outer_pupil_geometry cyl-y / cyl-x, lentil.h:387-388): the pack has none, so the
+    geometry is overridden on both sides; forward rays and reverse traces must still agree bit for bit."""
+    p = po_params(fstop=2.0, focus_dist=80.0)
+    o, r = orc.OracleCamera(p), ref.RefCamera(p)
+    o.set_pupil_geometry(outer)
+    r.set_pupil_geometry(outer)
+    n = 5000
+    ins = workloads.camera_samples(100, 50, 1, "cpu", 0, n, "linear")
+    arrs = [ins[k].numpy() for k in ("sx", "sy", "dsx", "dsy", "lensx", "lensy")]
+    a, b = o.create_rays(*arrs), r.create_rays(*arrs)
+    first = a["tries"] == 0
+    assert first.mean() > 0.5
+    for k in orc.RAY_OUT_FIELDS:
+        np.testing.assert_array_equal(a[k][:, first], b[k][:, first], err_msg=k)
+    O, R = orc.lib(), ref.lib()
+    rs = np.random.default_rng(11)
+    s1, s2 = (C.c_double * 2)(), (C.c_double * 2)()
+    for i in range(200):
+        tgt = (C.c_double * 3)(rs.uniform(-250, 250), rs.uniform(-150, 150), rs.uniform(200, 3000))
+        ok1 = O.orc_trace_ray_bw_po(o._h, tgt, 10 + i, 20, i, C.c_float(0.55), s1)
+        ok2 = R.ref_trace_ray_bw_po(r._h, tgt, 10 + i, 20, i, C.c_float(0.55), s2)
+        assert ok1 == ok2 and (not ok1 or list(s1) == list(s2))
