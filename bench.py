@@ -188,6 +188,7 @@ def main():
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-splat", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-thinlens", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -330,6 +331,9 @@ def main():
     launches = args.steps
     if not args.skip_splat:
         splat = bench_splat(args, rank, world, local_rank, dev, barrier, max_over_ranks, sum_over_ranks)
+    thin = None
+    if not args.skip_thinlens:
+        thin = bench_thinlens(args, rank, world, local_rank, dev, barrier, max_over_ranks, sum_over_ranks, hbm_peak)
 
     if rank == 0:
         line = {
@@ -345,7 +349,7 @@ def main():
                                                      "sample": f"{CPU_SAMPLE_PER_THREAD * (os.cpu_count() or 1)} rays on a coarser 16:9 pixel grid covering the same sensor, all host threads; "
                                                                + ("reference = /root/reference/src compiled behind oracle/shims (oracle/_ref)" if cpu["kind"] == "reference"
                                                                   else "port = oracle/lentil_oracle.cpp (FP64 restatement)")},
-            "splat": splat,
+            "splat": splat, "thinlens": thin,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -415,6 +419,74 @@ def bench_splat(args, rank, world, local_rank, dev, barrier, max_over_ranks, sum
             "splats_per_step": splats, "attempts_per_step": attempts, "newton_its_per_attempt": its / max(attempts, 1.0),
             "source_samples": SPLAT_W * SPLAT_H * spp, "tflops_algorithmic": flop / s / 1e12,
             "image_energy": float(img[..., :3].sum().item())}
+
+
+def bench_thinlens(args, rank, world, local_rank, dev, barrier, max_over_ranks, sum_over_ranks, hbm_peak):
+    """Thin-lens camera model (the reference's default camera_type): rays/s against the HBM
+    roofline (108 B/ray) and splats/s against the L2 reduction roofline on the same two frames."""
+    import ctypes
+
+    import torch
+
+    from pota_b200.camera import RAY_OUT_FIELDS, Camera, lib
+
+    spp = max(1, int(round(16 * args.frame_scale)))
+    n = FRAME_W * FRAME_H * spp
+    p = abi.CameraParams.defaults(camera_type=abi.LB_CAMERA_THINLENS, fstop=2.8, focus_dist=150.0, focal_length_lentil=50.0)
+    cam = Camera(p, device=local_rank)
+    ins = workloads.camera_samples(FRAME_W, FRAME_H, spp * world, dev, rank * n, n, "pixel")
+    out = {k: torch.empty((3, n), dtype=torch.float32, device=dev) for k in RAY_OUT_FIELDS}
+    stream = torch.cuda.current_stream()
+    args_in = [ins[k] for k in IN_KEYS]
+    for _ in range(2):
+        cam.create_rays(*args_in, ray_id_base=rank * n, out=out, stream=stream)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = max(1, args.steps)
+    e0.record(stream)
+    for _ in range(steps):
+        cam.create_rays(*args_in, ray_id_base=rank * n, out=out, stream=stream)
+    e1.record(stream)
+    barrier()
+    s = max_over_ranks(e0.elapsed_time(e1) * 1e-3) / steps
+    rays = {"value": world * n / s, "unit": "rays/s", "ms_per_step": s * 1e3, "rays_per_step_per_gpu": n,
+            "roofline": {"bound": "hbm", "achieved": n * 108 / s / 1e9, "peak": hbm_peak, "unit": "GB/s per GPU", "frac": n * 108 / s / 1e9 / hbm_peak,
+                         "bytes_per_ray": 108}}
+    del ins, out, args_in
+    torch.cuda.empty_cache()
+    # bidirectional, same synthetic frame as the PO splat bench
+    sspp = max(1, int(round(SPLAT_SPP * args.frame_scale)))
+    p2 = abi.CameraParams.defaults(camera_type=abi.LB_CAMERA_THINLENS, fstop=1.4, focus_dist=35.0, focal_length_lentil=50.0, bidir_sample_mult=10,
+                                   bokeh_enable_image=1)
+    cam2 = Camera(p2, bokeh=workloads.disc_bokeh_image(250), device=local_rank)
+    total = SPLAT_W * SPLAT_H * sspp
+    lo, hi = total * rank // world, total * (rank + 1) // world
+    fr = workloads.highlight_frame(SPLAT_W, SPLAT_H, sspp, cam2.state.tan_fov, dev, lo, hi - lo, grid=SPLAT_GRID)
+    aovs = [("RGBA", abi.LB_FILTER_GAUSSIAN, abi.LB_AOV_RGBA)]
+
+    def step():
+        cam2.filter_begin(SPLAT_W, SPLAT_H, aovs)
+        cam2.filter_accumulate(fr["px"], fr["py"], fr["rgba"], fr["pos_cs"], 1.0 / sspp, stream=stream)
+
+    step()
+    barrier()
+    e0.record(stream)
+    for _ in range(steps):
+        step()
+    e1.record(stream)
+    barrier()
+    s2 = max_over_ranks(e0.elapsed_time(e1) * 1e-3) / steps
+    st = cam2.filter_stats()
+    splats = sum_over_ranks(float(st["splats"]))
+    adds = splats + sum_over_ranks(float(st["passthrough"]))
+    red_peak = ctypes.c_double()
+    lib().lb_bench_red_peak(local_rank, 41, ctypes.byref(red_peak))
+    return {"rays": rays,
+            "splat": {"value": splats / s2, "unit": "splats/s", "ms_per_step": s2 * 1e3, "splats_per_step": splats, "accumulate_only": "no reduce/resolve in this leg",
+                      "roofline": {"bound": "l2_reduction", "achieved": adds * 20.0 / s2 / 1e9 / world, "peak": red_peak.value, "unit": "GB/s per GPU",
+                                   "frac": adds * 20.0 / s2 / 1e9 / world / max(red_peak.value, 1e-9)}},
+            "config": {"workload": f"ThinLens camera_type, focal 50 mm: rays {FRAME_W}x{FRAME_H}x{spp}spp per GPU f/2.8 focus 150; "
+                                   f"splats {SPLAT_W}x{SPLAT_H}x{sspp}spp highlight frame f/1.4 focus 35, 250x250 image-bokeh kernel"}}
 
 
 if __name__ == "__main__":

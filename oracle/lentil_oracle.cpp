@@ -196,6 +196,92 @@ V3 line_plane_intersection(V3 rayOrigin, V3 rayDirection) {  // lens.h:412-419
   return {rayOrigin.x + (rayDirection.x * s) / dn, rayOrigin.y + (rayDirection.y * s) / dn, rayOrigin.z + (rayDirection.z * s) / dn};
 }
 
+// ---- thin-lens helpers, lens.h:477-582 (float arithmetic, as there) ---------------------------------
+struct V3f { float x, y, z; };
+inline float dot3f(V3f a, V3f b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+inline V3f normalize3f(V3f a) {  // AiV3Normalize
+  float t = std::sqrt(dot3f(a, a));
+  if (t != 0) t = 1 / t;
+  return {a.x * t, a.y * t, a.z * t};
+}
+inline float ai_bias(float a, float b) {  // AiBias [EXTERNAL, as oracle/shims/ai.h]
+  return (a > 0) ? ((b > 0) ? std::pow(a, std::log(b) / std::log(0.5f)) : 0) : 0;
+}
+void concentricDiskSample(float ox, float oy, V2 &lens, float bias, float squarelerp, float /*squeeze_x*/) {  // lens.h:477-517
+  if (ox == 0.0 && oy == 0.0) { lens.x = 0.0; lens.y = 0.0; return; }
+  float phi, r;
+  const float a = 2.0 * ox - 1.0;
+  const float b = 2.0 * oy - 1.0;
+  if ((a * a) > (b * b)) { r = a; phi = 0.78539816339 * (b / a); }
+  else { r = b; phi = (1.57079632679489661923f) - ((0.78539816339) * (a / b)); }
+  if (bias != 0.5) r = ai_bias(std::abs(r), bias) * (r < 0 ? -1 : 1);
+  const float cos_phi = fast_cos(phi);
+  const float sin_phi = fast_sin(phi);
+  lens.x = r * cos_phi;
+  lens.y = r * sin_phi;
+  if (squarelerp > 0.0) {
+    lens.x = linear_interpolate(squarelerp, lens.x, a);
+    lens.y = linear_interpolate(squarelerp, lens.y, b);
+  }
+}
+bool empericalOpticalVignettingSquare(V3f origin, V3f direction, float apertureRadius, float opticalVignettingRadius,
+                                      float opticalVignettingDistance, float squarebias) {  // lens.h:532-541
+  float intersection = std::abs(opticalVignettingDistance / direction.z);
+  V3f p{direction.x * intersection - origin.x, direction.y * intersection - origin.y, direction.z * intersection - origin.z};
+  float power = 1.0 + squarebias;
+  float radius = apertureRadius * opticalVignettingRadius;
+  float dist = std::pow(std::abs(p.x), power) + std::pow(std::abs(p.y), power);
+  return !(dist > std::pow(radius, power));
+}
+inline float lerp_squircle_mapping(float amount) { return 1.0 + std::log(1.0 + amount) * std::exp(amount * 3.0); }  // lens.h:544-546
+inline void barrelDistortion(float &ux, float &uy, float distortion) {  // lens.h:548-551: uv *= 1. + dot(uv,uv)*distortion
+  const float f = 1. + (ux * ux + uy * uy) * distortion;
+  ux *= f; uy *= f;
+}
+inline void inverseBarrelDistortion(float &ux, float &uy, float distortion) {  // lens.h:553-562
+  float b = distortion;
+  float l = std::sqrt(ux * ux + uy * uy);
+  float x0 = std::pow(9. * b * b * l + std::sqrt(3.) * std::sqrt(27. * b * b * b * b * l * l + 4. * b * b * b), 1. / 3.);
+  float x = x0 / (std::pow(2., 1. / 3.) * std::pow(3., 2. / 3.) * b) - std::pow(2. / 3., 1. / 3.) / x0;
+  const float f = x / l;
+  ux *= f; uy *= f;
+}
+float abb_coma_multipliers(const float sensor_width, const float focal_length, const V3f dir_from_center, const V2 unit_disk) {  // lens.h:566-574
+  const V3f maximal_perturbed_ray{(float)(1.0 * (sensor_width * 0.5)), (float)(1.0 * (sensor_width * 0.5)), -focal_length};
+  float maximal_projection = dot3f(normalize3f(maximal_perturbed_ray), V3f{0.0f, 0.0f, -1.0f});
+  float current_projection = dot3f(dir_from_center, V3f{0.0f, 0.0f, -1.0f});
+  float projection_perc = ((current_projection - maximal_projection) / (1.0 - maximal_projection) - 0.5) * 2.0;
+  float dist_from_sensor_center = 1.0 - projection_perc;
+  float dist_from_aperture = std::sqrt(unit_disk.x * unit_disk.x + unit_disk.y * unit_disk.y);  // Eigen norm(), double -> float
+  return dist_from_sensor_center * dist_from_aperture;
+}
+V3f abb_coma_perturb(const V3f dir_from_lens, const V3f ray_to_perturb, const float abb_coma, const bool reverse) {  // lens.h:578-586
+  const V3f c{dir_from_lens.y * -1.0f - dir_from_lens.z * 0.0f, dir_from_lens.z * 0.0f - dir_from_lens.x * -1.0f,
+              dir_from_lens.x * 0.0f - dir_from_lens.y * 0.0f};  // AiV3Cross(dir_from_lens, (0,0,-1))
+  const V3f axis_tmp = normalize3f(c);
+  const double ax = axis_tmp.x, ay = axis_tmp.y, az = axis_tmp.z;
+  const double angle = (abb_coma * 2.3456 * AI_PI_F) / 180.0;
+  const double co = std::cos(angle), si = std::sin(angle), t = 1.0 - co;
+  double m[3][3] = {{t * ax * ax + co, t * ax * ay - si * az, t * ax * az + si * ay},
+                    {t * ax * ay + si * az, t * ay * ay + co, t * ay * az - si * ax},
+                    {t * ax * az - si * ay, t * ay * az + si * ax, t * az * az + co}};
+  if (reverse) {  // rot.inverse(): general 3x3 inverse, as the Eigen stand-in of oracle/_ref does
+    const double (*a)[3] = m;
+    const double det = a[0][0] * (a[1][1] * a[2][2] - a[1][2] * a[2][1]) - a[0][1] * (a[1][0] * a[2][2] - a[1][2] * a[2][0]) +
+                       a[0][2] * (a[1][0] * a[2][1] - a[1][1] * a[2][0]);
+    double r[3][3];
+    r[0][0] = (a[1][1] * a[2][2] - a[1][2] * a[2][1]) / det; r[0][1] = (a[0][2] * a[2][1] - a[0][1] * a[2][2]) / det;
+    r[0][2] = (a[0][1] * a[1][2] - a[0][2] * a[1][1]) / det; r[1][0] = (a[1][2] * a[2][0] - a[1][0] * a[2][2]) / det;
+    r[1][1] = (a[0][0] * a[2][2] - a[0][2] * a[2][0]) / det; r[1][2] = (a[0][2] * a[1][0] - a[0][0] * a[1][2]) / det;
+    r[2][0] = (a[1][0] * a[2][1] - a[1][1] * a[2][0]) / det; r[2][1] = (a[0][1] * a[2][0] - a[0][0] * a[2][1]) / det;
+    r[2][2] = (a[0][0] * a[1][1] - a[0][1] * a[1][0]) / det;
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) m[i][j] = r[i][j];
+  }
+  const double rx = ray_to_perturb.x, ry = ray_to_perturb.y, rz = ray_to_perturb.z;
+  return {(float)(m[0][0] * rx + m[0][1] * ry + m[0][2] * rz), (float)(m[1][0] * rx + m[1][1] * ry + m[1][2] * rz),
+          (float)(m[2][0] * rx + m[2][1] * ry + m[2][2] * rz)};
+}
+
 // ---- imagebokeh.h ---------------------------------------------------------------------------
 struct arrayCompare {  // imagebokeh.h:21-27
   const float *values;
@@ -338,6 +424,9 @@ struct orc_camera {
   double lambda = 0.55;
   float extra_sensor_shift = 0, focal_length = 35;
   float abb_chromatic = 0;
+  int abb_chromatic_type = 0;
+  float optical_vignetting_distance = 0, optical_vignetting_radius = 1.0f;
+  float abb_spherical = 0.5f, abb_coma = 0, abb_distortion = 0, circle_to_square = 0.01f, bokeh_anamorphic = 1.0f;
   float fov = 0;
   double tan_fov = 0, aperture_radius = 0, sensor_shift = 0;
   unsigned xres = 0, yres = 0, xres_without_region = 0, yres_without_region = 0;
@@ -600,20 +689,91 @@ struct orc_camera {
       weight[0] = weight[1] = weight[2] = 0.0f;
   }
 
+  inline float get_image_dist_focusdist_thinlens() {  // lentil.h:664-666
+    return (-focal_length * -focus_distance) / (-focal_length + -focus_distance);
+  }
+  inline float get_image_dist_focusdist_thinlens_abberated(const float shift) {  // lentil.h:668-670
+    return (-focal_length * -(focus_distance + shift)) / (-focal_length + -(focus_distance + shift));
+  }
+
+  // unit disk sample of the thin-lens paths (lentil.h:457-472, lentil_filter.cpp:316-322)
+  void thinlens_unit_disk(double r1, double r2, V2 &unit_disk) {
+    if (bokeh_enable_image) image.bokehSample(r1, r2, unit_disk);
+    else if (bokeh_aperture_blades < 2) concentricDiskSample(r1, r2, unit_disk, abb_spherical, circle_to_square, bokeh_anamorphic);
+    else lens_sample_triangular_aperture(unit_disk.x, unit_disk.y, r1, r2, 1.0, bokeh_aperture_blades);
+  }
+
+  // lentil.h:431-569.  Same retry-RNG substitution as trace_ray_fw_po.
+  void trace_ray_fw_thinlens(int &tries, const double sx, const double sy, float origin[3], float dir[3], float weight[3], double &r1,
+                             double &r2, const bool deriv_ray, uint32_t ray_id) {
+    tries = 0;
+    bool ray_succes = false;
+    while (!ray_succes && tries <= vignetting_retries) {
+      float s0 = sx, s1 = sy;  // AtVector s(sx, sy, 0.0)
+      if (abb_distortion > 0.0) { s0 = sx; s1 = sy; barrelDistortion(s0, s1, abb_distortion); }
+      const V3f p{(float)(s0 * (sensor_width * 0.5)), (float)(s1 * (sensor_width * 0.5)), -focal_length};
+      V3f dir_from_center = normalize3f(p);
+      V2 unit_disk{0, 0};
+      if (enable_dof) {
+        if (!deriv_ray && tries > 0) {
+          unsigned int seed = tea<8>(ray_id, (unsigned int)tries);
+          r1 = rng(seed);
+          r2 = rng(seed);
+        }
+        thinlens_unit_disk(r1, r2, unit_disk);
+      }
+      unit_disk.x *= bokeh_anamorphic;
+      float abb_field_curvature = 0.0;
+      V3f lens{(float)(unit_disk.x * aperture_radius), (float)(unit_disk.y * aperture_radius), 0.0f};
+      const float intersection = std::abs(focus_distance / linear_interpolate(abb_field_curvature, dir_from_center.z, 1.0));
+      const V3f focusPoint{dir_from_center.x * intersection, dir_from_center.y * intersection, dir_from_center.z * intersection};
+      V3f dir_from_lens = normalize3f(V3f{focusPoint.x - lens.x, focusPoint.y - lens.y, focusPoint.z - lens.z});
+      float abb_coma_multiplied = abb_coma * abb_coma_multipliers(sensor_width, focal_length, dir_from_center, unit_disk);
+      dir_from_lens = abb_coma_perturb(dir_from_lens, dir_from_lens, abb_coma_multiplied, false);
+      if (optical_vignetting_distance > 0.0 && !deriv_ray) {
+        if (!empericalOpticalVignettingSquare(lens, dir_from_lens, aperture_radius, optical_vignetting_radius, optical_vignetting_distance,
+                                              lerp_squircle_mapping(circle_to_square))) {
+          ++tries;
+          continue;
+        }
+      }
+      origin[0] = lens.x; origin[1] = lens.y; origin[2] = lens.z;
+      dir[0] = dir_from_lens.x; dir[1] = dir_from_lens.y; dir[2] = dir_from_lens.z;
+      float s = 1.0f;  // lentil.h:538-560
+      switch (unitModel) {
+        case LB_UNITS_MM: s = (float)10.0; break;
+        case LB_UNITS_CM: s = (float)1.0; break;
+        case LB_UNITS_DM: s = (float)0.1; break;
+        case LB_UNITS_M: s = (float)0.01; break;
+      }
+      for (int k = 0; k < 3; ++k) { origin[k] *= s; dir[k] *= s; }
+      ray_succes = true;
+    }
+    const V3f d = normalize3f(V3f{dir[0], dir[1], dir[2]});
+    dir[0] = d.x; dir[1] = d.y; dir[2] = d.z;
+    if (!ray_succes) weight[0] = weight[1] = weight[2] = 0.0f;
+  }
+
+  void trace_ray_fw(int &tries, const double sx, const double sy, float origin[3], float direction[3], float weight[3], double &r1,
+                    double &r2, const bool deriv_ray, uint32_t ray_id) {  // lentil_camera.cpp:90-94
+    if (cameraType == LB_CAMERA_THINLENS) trace_ray_fw_thinlens(tries, sx, sy, origin, direction, weight, r1, r2, deriv_ray, ray_id);
+    else trace_ray_fw_po(tries, sx, sy, origin, direction, weight, r1, r2, deriv_ray, ray_id);
+  }
+
   // lentil_camera.cpp:78-125
   void camera_create_ray(float sx, float sy, float dsx, float dsy, float lensx, float lensy, uint32_t ray_id, float *o /*21*/, int *tries_out) {
     int tries = 0;
     double r1 = lensx, r2 = lensy;
     const float step = 0.001;
     float origin[3] = {0, 0, 0}, direction[3] = {0, 0, 0}, weight[3] = {1, 1, 1};
-    trace_ray_fw_po(tries, sx, sy, origin, direction, weight, r1, r2, false, ray_id);
+    trace_ray_fw(tries, sx, sy, origin, direction, weight, r1, r2, false, ray_id);
     if (tries_out) *tries_out = tries;
     float input_dx_sx = sx + (dsx * step);
     float input_dx_sy = sy + (dsy * step);
     float odxo[3] = {0, 0, 0}, odyo[3] = {0, 0, 0}, odxd[3] = {0, 0, 0}, odyd[3] = {0, 0, 0};
     float wdx[3] = {1, 1, 1}, wdy[3] = {1, 1, 1};
-    trace_ray_fw_po(tries, input_dx_sx, sy, odxo, odxd, wdx, r1, r2, true, ray_id);
-    trace_ray_fw_po(tries, sx, input_dx_sy, odyo, odyd, wdy, r1, r2, true, ray_id);
+    trace_ray_fw(tries, input_dx_sx, sy, odxo, odxd, wdx, r1, r2, true, ray_id);
+    trace_ray_fw(tries, sx, input_dx_sy, odyo, odyd, wdy, r1, r2, true, ray_id);
     const float inv_step = 1.0f / step;  // AtVector::operator/(float) multiplies by the reciprocal [EXTERNAL, as oracle/shims/ai.h]
     for (int k = 0; k < 3; ++k) {
       o[0 + k] = origin[k];
@@ -787,13 +947,82 @@ struct orc_camera {
       for (int k = 0; k < 4; ++k) aov_values[4 * a + k] = src[k];
     }
     ++stats.samples;
-    if (std::abs(csp[2]) < (lens_length * 0.1)) redistribute = false;  // :240
+    if (cameraType == LB_CAMERA_POLYNOMIAL_OPTICS && std::abs(csp[2]) < (lens_length * 0.1)) redistribute = false;  // :240 (PO case only)
     if (redistribute == false) {
       filter_and_add_to_buffer_new(px, py, depth, aov_values, inverse_sample_density);
       ++stats.passthrough;
       return;
     }
     ++stats.redistributed;
+    if (cameraType == LB_CAMERA_THINLENS) {  // lentil_filter.cpp:303-447
+      const V3f P{csp[0], csp[1], csp[2]};
+      for (int count = 0; count < samples && total_samples_taken < max_total_samples; ++count, ++total_samples_taken) {
+        ++stats.attempts;
+        unsigned int seed = tea<8>((px * py + px), total_samples_taken);
+        float image_dist_samplepos = (-focal_length * P.z) / (-focal_length + P.z);
+        V2 unit_disk{0, 0};
+        // argument evaluation order of g++ (right to left), as in trace_ray_bw_po
+        if (bokeh_enable_image) { float s2 = rng(seed), s1 = rng(seed), col = rng(seed), row = rng(seed); (void)s1; (void)s2; image.bokehSample(row, col, unit_disk); }
+        else if (bokeh_aperture_blades < 2) { float oy = rng(seed), ox = rng(seed); concentricDiskSample(ox, oy, unit_disk, abb_spherical, circle_to_square, bokeh_anamorphic); }
+        else { float b = rng(seed), a = rng(seed); lens_sample_triangular_aperture(unit_disk.x, unit_disk.y, a, b, 1.0, bokeh_aperture_blades); }
+        unit_disk.x *= bokeh_anamorphic;
+        V3f lens{(float)(unit_disk.x * aperture_radius), (float)(unit_disk.y * aperture_radius), 0.0f};
+        V3f dir_from_center = normalize3f(P);
+        V3f dir_lens_to_P = normalize3f(V3f{P.x - lens.x, P.y - lens.y, P.z - lens.z});
+        float abb_coma_multiplied = abb_coma * abb_coma_multipliers(sensor_width, focal_length, dir_from_center, unit_disk);
+        dir_lens_to_P = abb_coma_perturb(dir_lens_to_P, dir_from_center, abb_coma_multiplied, true);
+        const float lenP = std::sqrt(dot3f(P, P));
+        V3f P_perturbed{lenP * dir_lens_to_P.x, lenP * dir_lens_to_P.y, lenP * dir_lens_to_P.z};
+        dir_from_center = normalize3f(P_perturbed);
+        float samplepos_image_intersection = std::abs(image_dist_samplepos / dir_from_center.z);
+        V3f samplepos_image_point{dir_from_center.x * samplepos_image_intersection, dir_from_center.y * samplepos_image_intersection,
+                                  dir_from_center.z * samplepos_image_intersection};
+        V3f dir_img = normalize3f(V3f{samplepos_image_point.x - lens.x, samplepos_image_point.y - lens.y, samplepos_image_point.z - lens.z});
+        float focusdist_intersection_unperturbed = std::abs(get_image_dist_focusdist_thinlens() / dir_img.z);
+        V3f fu{lens.x + dir_img.x * focusdist_intersection_unperturbed, lens.y + dir_img.y * focusdist_intersection_unperturbed,
+               lens.z + dir_img.z * focusdist_intersection_unperturbed};
+        const float spu_x = fu.x / fu.z, spu_y = fu.y / fu.z;
+        const float distance_to_center_unperturbed = std::sqrt((0.0f - spu_x) * (0.0f - spu_x) + (0.0f - spu_y) * (0.0f - spu_y));
+        // (occlusion probe: no scene, never occluded)
+        if (optical_vignetting_distance > 0.0) {
+          dir_lens_to_P = normalize3f(V3f{P_perturbed.x - lens.x, P_perturbed.y - lens.y, P_perturbed.z - lens.z});
+          if (!empericalOpticalVignettingSquare(lens, dir_lens_to_P, aperture_radius, optical_vignetting_radius, optical_vignetting_distance,
+                                                lerp_squircle_mapping(circle_to_square))) {
+            --count;
+            continue;
+          }
+        }
+        float focusdist_intersection = std::abs(get_image_dist_focusdist_thinlens() / dir_img.z);
+        float rgb_weight[3] = {1, 1, 1};
+        if (abb_chromatic > 0.0) {
+          const float abb_chromatic_lateral = 5.0;
+          // the reference draws the channel from the process-global xor128 and keeps the counter-RNG variant in a
+          // comment (lentil_filter.cpp:395-396); the counter variant is used here and in the product (stated deviation)
+          const int channel = static_cast<int>(rng(seed) * 3) - 1;
+          rgb_weight[0] = channel == -1 ? 3 : 0; rgb_weight[1] = channel == 0 ? 3 : 0; rgb_weight[2] = channel == 1 ? 3 : 0;
+          float direction_shift = abb_chromatic_type == 0 ? std::abs(channel) : channel;
+          focusdist_intersection = std::abs(get_image_dist_focusdist_thinlens_abberated(direction_shift * abb_chromatic * abb_chromatic_lateral * distance_to_center_unperturbed) / dir_img.z);
+        }
+        V3f fp{lens.x + dir_img.x * focusdist_intersection, lens.y + dir_img.y * focusdist_intersection, lens.z + dir_img.z * focusdist_intersection};
+        float sp_x = fp.x / fp.z, sp_y = fp.y / fp.z;
+        {  // sensor_position /= (sensor_width*0.5)/-focal_length : AtVector2::operator/=(float), reciprocal multiply [EXTERNAL]
+          const float div = (sensor_width * 0.5) / -focal_length;
+          const float c = 1.0f / div;
+          sp_x *= c; sp_y *= c;
+        }
+        if (abb_distortion > 0.0) inverseBarrelDistortion(sp_x, sp_y, abb_distortion);
+        const double s0 = sp_x, s1 = sp_y * frame_aspect_ratio_without_region;
+        const float pixel_x = (((s0 + 1.0) / 2.0) * xres_without_region) - region_min_x;
+        const float pixel_y = (((-s1 + 1.0) / 2.0) * yres_without_region) - region_min_y;
+        if ((pixel_x >= xres_d) || (pixel_x < 0) || (pixel_y >= yres_d) || (pixel_y < 0)) { --count; continue; }
+        unsigned pixelnumber = (unsigned)((int)std::floor(pixel_x) + ((int)std::floor(pixel_y) * xres));
+        float filter_weight = 1.0;
+        for (size_t a = 0; a < aovs.size(); ++a)
+          add_to_buffer(aovs[a], pixelnumber, &aov_values[4 * a], fitted_bidir_add_energy, depth, filter_weight * inverse_sample_density * inv_samples, rgb_weight);
+        ++stats.splats;
+      }
+      return;
+    }
     for (int count = 0; count < samples && total_samples_taken < max_total_samples; ++count, ++total_samples_taken) {
       V2 sensor_position{0, 0};
       float lambda_per_sample = 0.55;
@@ -910,6 +1139,15 @@ struct orc_camera {
     extra_sensor_shift = p->extra_sensor_shift;
     focal_length = clamp_min_f(p->focal_length_lentil, 0.01);
     abb_chromatic = p->abb_chromatic;
+    // thin-lens parameters, lentil.h:1217-1229
+    optical_vignetting_distance = p->optical_vignetting;
+    optical_vignetting_radius = 1.0;
+    abb_spherical = clamp_f(p->abb_spherical, 0.001, 0.999);
+    abb_distortion = p->abb_distortion;
+    abb_coma = p->abb_coma;
+    abb_chromatic_type = p->abb_chromatic_type;
+    circle_to_square = clamp_f(p->bokeh_circle_to_square, 0.01, 0.99);
+    bokeh_anamorphic = clamp_f(1.0 - p->bokeh_anamorphic, 0, 1.0);
     bokeh_enable_image = p->bokeh_enable_image != 0;
     bidir_sample_mult = p->bidir_sample_mult;
     bidir_add_energy_minimum_luminance = p->bidir_add_energy_minimum_luminance;

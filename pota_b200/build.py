@@ -31,6 +31,7 @@ UNITS = {
     "filter_kernels.cu": [],
     "setup_kernels.cu": ["-fmad=false"],
     "filter_classify.cu": ["-fmad=false"],
+    "thinlens_kernels.cu": ["-fmad=false"],
     "lentil_host.cu": [],
     "filter_host.cu": ["-I", "/usr/include"],
     "microbench.cu": [],

@@ -75,8 +75,7 @@ k_filter_classify(const __grid_constant__ FilterConsts fc, const __grid_constant
     if (sf > 2000.f) sf = 2000.f;
     samples = (int)sf;
     const float debug_val = (float)(samples * (redistribute ? 1 : 0));  // lentil_debug value, taken at :209-211
-    if ((double)fabsf(csp[2]) < fc.lens_length_tenth) redistribute = false;  // :240
-    if (fc.camera_type != 1) redistribute = false;  // only the PolynomialOptics branch is built
+    if (fc.camera_type == 1 && (double)fabsf(csp[2]) < fc.lens_length_tenth) redistribute = false;  // :240, PolynomialOptics case only
     const int px = __ldg(s.px + i), py = __ldg(s.py + i);
     if (!redistribute) {
       // filter_and_add_to_buffer_new (lentil.h:938-955): every AOV, own pixel, weight inv_density

@@ -22,6 +22,7 @@ const lb_camera_state &cam_state(lb_camera *c);
 const LensTable &cam_lens(lb_camera *c);
 int cam_lens_kernel(lb_camera *c);
 const CamConsts<float> &cam_consts(lb_camera *c);
+const ThinConsts &cam_thin(lb_camera *c);
 struct FilterStateTag;
 std::mutex &cam_mutex(lb_camera *c);
 int lb_fail(int code, const char *msg);
@@ -166,8 +167,11 @@ int accumulate_device(lb_camera *c, FilterState *f, const lb_samples *S, cudaStr
               (const float4 *)S->transmission, S->flags, S->inv_density};
   CUF(cudaMemsetAsync(&f->d_counters->work_count, 0, 2 * sizeof(unsigned), stream));
   CUF(launch_filter_classify(fc, A, io, f->work, f->d_counters, f->sample_base, stream));
-  CUF(launch_filter_splat(cam_lens_kernel(c), cam_lens(c), cam_consts(c), fc, A, io, f->work, f->d_counters, f->sample_base,
-                          cam_num_sms(c), stream));
+  if (cam_params(c).camera_type == LB_CAMERA_THINLENS)
+    CUF(launch_filter_splat_thinlens(cam_consts(c), cam_thin(c), fc, A, io, f->work, f->d_counters, f->sample_base, cam_num_sms(c), stream));
+  else
+    CUF(launch_filter_splat(cam_lens_kernel(c), cam_lens(c), cam_consts(c), fc, A, io, f->work, f->d_counters, f->sample_base,
+                            cam_num_sms(c), stream));
   if (f->has_closest || f->has_debug_closest) CUF(launch_closest_gather(fc, A, io, f->sample_base, stream));
   f->sample_base += S->n;
   return LB_OK;

@@ -184,6 +184,7 @@ struct lb_camera {
   // that noise below the reference's own quantisation (measured: profiles/r01_differentials.txt).
   float deriv_baseline = 16.0f;
   CamConsts<float> camf{};
+  ThinConsts thin{};
   CamConsts<double> camd{};
   // bokeh CDF on device
   float *d_cdf_row = nullptr, *d_cdf_col = nullptr;
@@ -235,6 +236,39 @@ void refresh_consts(lb_camera *c) {
   };
   fill(c->camf);
   fill(c->camd);
+  // thin-lens scalars (get_lentil_camera_params lentil.h:1216-1229; constants hoisted out of the per-ray code)
+  ThinConsts &t = c->thin;
+  auto clampf = [](float in, const float mn, const float mx) { if (in < mn) in = mn; if (in > mx) in = mx; return in; };  // global.h:8-12
+  t.sensor_half = (double)p.sensor_width * 0.5;
+  t.focus_distance = s.focus_distance;
+  t.aperture_radius = s.aperture_radius;
+  t.focal_length = clamp_min_f(p.focal_length_lentil, 0.01);
+  t.abb_spherical = clampf(p.abb_spherical, 0.001, 0.999);
+  t.circle_to_square = clampf(p.bokeh_circle_to_square, 0.01, 0.99);
+  t.bokeh_anamorphic = clampf(1.0 - p.bokeh_anamorphic, 0, 1.0);
+  t.abb_coma = p.abb_coma;
+  t.abb_distortion = p.abb_distortion;
+  t.abb_chromatic = p.abb_chromatic;
+  t.abb_chromatic_type = p.abb_chromatic_type;
+  t.optical_vignetting_distance = p.optical_vignetting;
+  t.optical_vignetting_radius = 1.0f;
+  t.squircle = 1.0 + std::log(1.0 + t.circle_to_square) * std::exp(t.circle_to_square * 3.0);  // lerp_squircle_mapping, lens.h:544-546
+  {  // maximal_projection of abb_coma_multipliers (lens.h:567-568), float arithmetic as there
+    const float sw = p.sensor_width;
+    const float mx = (float)(1.0 * (sw * 0.5)), mz = -t.focal_length;
+    float len = std::sqrt(mx * mx + mx * mx + mz * mz);
+    if (len != 0) len = 1 / len;
+    t.coma_max_projection = (mx * len) * 0.0f + (mx * len) * 0.0f + (mz * len) * -1.0f;
+  }
+  t.image_dist_focusdist = (-t.focal_length * -t.focus_distance) / (-t.focal_length + -t.focus_distance);  // lentil.h:664-666
+  const float tl_scales[4] = {(float)10.0, (float)1.0, (float)0.1, (float)0.01};
+  t.unit_scale = tl_scales[std::min(std::max(p.units, 0), 3)];
+}
+
+// camera_create_ray dispatch on cameraType (lentil_camera.cpp:90-94)
+cudaError_t launch_rays(lb_camera *c, const RayIO &io, size_t n, uint64_t ray_id_base, cudaStream_t stream) {
+  if (c->params.camera_type == LB_CAMERA_THINLENS) return launch_create_rays_thinlens(c->camf, c->thin, io, n, ray_id_base, stream);
+  return launch_create_rays(c->lens_kernel, c->lens, c->camf, io, n, ray_id_base, stream);
 }
 
 // get_lentil_camera_params (lentil.h:1189-1243) + camera_model_specific_setup (lentil.h:1568-1670)
@@ -342,7 +376,7 @@ int camera_setup(lb_camera *c, const lb_camera_params *p, const lb_bokeh_image *
       cudaFree(d_out);
     }
     s.tan_fov = std::tan(s.lens_field_of_view / 2.0);
-  } else {  // ThinLens (lentil.h:1663-1668): only the scalars get_coc_thinlens needs; rays are not traced
+  } else {  // ThinLens (lentil.h:1663-1668)
     const float fov = 2.0 * std::atan(p->sensor_width / (2.0 * focal_length));
     s.tan_fov = std::tan(fov / 2.0);
     s.aperture_radius = (focal_length / (2.0 * input_fstop)) / 10.0;
@@ -471,11 +505,10 @@ int lb_camera_create_rays(lb_camera *c, size_t n, uint64_t ray_id_base, const lb
   if (!c || !in || !out) return fail(LB_ERR_INVALID, "null argument");
   if (n == 0) return LB_OK;
   if (!in->sx || !in->sy || !in->dsx || !in->dsy || !in->lensx || !in->lensy) return fail(LB_ERR_INVALID, "null input array");
-  if (c->params.camera_type != LB_CAMERA_POLYNOMIAL_OPTICS) return fail(LB_ERR_STATE, "camera_type ThinLens is not traced by this build");
   DeviceGuard g(c->device);
   RayIO io{in->sx, in->sy, in->dsx, in->dsy, in->lensx, in->lensy, out->origin, out->dir, out->dOdx, out->dOdy,
            out->dDdx, out->dDdy, out->weight, out->tries, n};
-  CU(launch_create_rays(c->lens_kernel, c->lens, c->camf, io, n, ray_id_base, (cudaStream_t)stream));
+  CU(launch_rays(c, io, n, ray_id_base, (cudaStream_t)stream));
   return LB_OK;
 }
 
@@ -486,7 +519,6 @@ int lb_camera_create_rays_host(lb_camera *c, size_t n, uint64_t ray_id_base, con
   if (!c || !in || !out) return fail(LB_ERR_INVALID, "null argument");
   if (n == 0) return LB_OK;
   if (!in->sx || !in->sy || !in->dsx || !in->dsy || !in->lensx || !in->lensy) return fail(LB_ERR_INVALID, "null input array");
-  if (c->params.camera_type != LB_CAMERA_POLYNOMIAL_OPTICS) return fail(LB_ERR_STATE, "camera_type ThinLens is not traced by this build");
   std::lock_guard<std::mutex> lk(c->mu);
   DeviceGuard g(c->device);
   const size_t chunk = std::min<size_t>(std::max<size_t>(n, 1), (size_t)1 << 21);  // 2 Mi rays: 48 MB in, 176 MB out per slot
@@ -517,7 +549,7 @@ int lb_camera_create_rays_host(lb_camera *c, size_t n, uint64_t ray_id_base, con
     for (int v = 0; v < 7; ++v) *slots[v] = dst[v] ? o + (size_t)v * 3 * chunk : nullptr;
     io.tries = out->tries ? (int32_t *)(o + 21 * chunk) : nullptr;
     io.plane = chunk;
-    CU(launch_create_rays(c->lens_kernel, c->lens, c->camf, io, m, ray_id_base + base, st));
+    CU(launch_rays(c, io, m, ray_id_base + base, st));
     for (int v = 0; v < 7; ++v)
       if (dst[v])  // 3 planes of the chunk -> 3 plane ranges of the user's [3][n] array: one strided copy
         CU(cudaMemcpy2DAsync(dst[v] + base, n * sizeof(float), o + (size_t)v * 3 * chunk, chunk * sizeof(float), m * sizeof(float), 3,
@@ -546,6 +578,7 @@ const lb_camera_state &cam_state(lb_camera *c) { return c->st; }
 const LensTable &cam_lens(lb_camera *c) { return c->lens; }
 int cam_lens_kernel(lb_camera *c) { return c->lens_kernel; }
 const CamConsts<float> &cam_consts(lb_camera *c) { return c->camf; }
+const ThinConsts &cam_thin(lb_camera *c) { return c->thin; }
 FilterState *&cam_filter(lb_camera *c) { return c->filter; }
 std::mutex &cam_mutex(lb_camera *c) { return c->mu; }
 int lb_fail(int code, const char *msg) { return fail(code, "%s", msg); }

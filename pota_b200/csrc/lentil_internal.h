@@ -26,6 +26,33 @@ cudaError_t launch_focus_distances(const LensTable &lens, const CamConsts<double
 cudaError_t launch_fstop_rays(const LensTable &lens, const CamConsts<double> &cam, int n, double outer_pupil_radius, double4 *out,
                               cudaStream_t stream);
 
+// ---- thin-lens path (thinlens_kernels.cu): trace_ray_fw_thinlens lentil.h:431-569, filter ThinLens branch
+// lentil_filter.cpp:303-447.  Scalars of struct Camera the thin-lens code reads, types as in the reference.
+struct ThinConsts {
+  double sensor_half;       // sensor_width * 0.5
+  double focus_distance;
+  double aperture_radius;
+  float focal_length;
+  float abb_spherical, circle_to_square, bokeh_anamorphic;
+  float abb_coma, abb_distortion, abb_chromatic;
+  int32_t abb_chromatic_type;
+  float optical_vignetting_distance, optical_vignetting_radius;
+  float squircle;              // lerp_squircle_mapping(circle_to_square), lens.h:544-546 (host libm)
+  float coma_max_projection;   // maximal_projection of abb_coma_multipliers, lens.h:567-568
+  float image_dist_focusdist;  // get_image_dist_focusdist_thinlens(), lentil.h:664-666
+  float unit_scale;            // 10, 1, 0.1, 0.01 (lentil.h:538-560)
+};
+struct FilterConsts;
+struct AovSet;
+struct SampleIO;
+struct WorkItem;
+struct FilterCounters;
+cudaError_t launch_create_rays_thinlens(const CamConsts<float> &cam, const ThinConsts &tl, const RayIO &io, size_t n, uint64_t ray_id_base,
+                                        cudaStream_t stream);
+cudaError_t launch_filter_splat_thinlens(const CamConsts<float> &cam, const ThinConsts &tl, const FilterConsts &fc, const AovSet &aovs,
+                                         const SampleIO &s, const WorkItem *work, FilterCounters *counters, uint64_t sample_base, int num_sms,
+                                         cudaStream_t stream);
+
 // ---- K2/K3 (filter_kernels.cu) ------------------------------------------------------------------
 struct FilterConsts {
   int32_t xres, yres, xres_full, yres_full, region_min_x, region_min_y;

@@ -237,3 +237,64 @@ def test_cylindrical_outer_pupil(outer):
         ok1 = O.orc_trace_ray_bw_po(o._h, tgt, 10 + i, 20, i, C.c_float(0.55), s1)
         ok2 = R.ref_trace_ray_bw_po(r._h, tgt, 10 + i, 20, i, C.c_float(0.55), s2)
         assert ok1 == ok2 and (not ok1 or list(s1) == list(s2))
+
+
+# ---- thin-lens path: trace_ray_fw_thinlens lentil.h:431-569, filter ThinLens branch lentil_filter.cpp:303-447
+TL_CASES = [
+    dict(),
+    dict(fstop=1.4, focus_dist=80.0, focal_length_lentil=50.0),
+    dict(abb_coma=0.6, abb_distortion=0.3, optical_vignetting=2.0, bokeh_circle_to_square=0.5, bokeh_anamorphic=0.3),
+    dict(abb_spherical=0.3, aperture_blades_lentil=6),
+    dict(bokeh_enable_image=1, units=abi.LB_UNITS_M, abb_coma=0.2),
+]
+
+
+def _tl_params(**kw):
+    base = dict(camera_type=abi.LB_CAMERA_THINLENS, fstop=2.8, focus_dist=150.0)
+    base.update(kw)
+    return abi.CameraParams.defaults(**base)
+
+
+@pytest.mark.parametrize("kw", TL_CASES)
+def test_thinlens_camera_create_ray(kw):
+    img = workloads.disc_bokeh_image(64) if kw.get("bokeh_enable_image") else None
+    p = _tl_params(**kw)
+    o, r = orc.OracleCamera(p, img), ref.RefCamera(p, img)
+    assert o.state.aperture_radius == r.state.aperture_radius and o.state.tan_fov == r.state.tan_fov
+    n = 20000
+    w = int(round((n * 16 / 9) ** 0.5))
+    ins = workloads.camera_samples(w, -(-n // w), 1, "cpu", 0, n, "linear")
+    arrs = [ins[k].numpy() for k in ("sx", "sy", "dsx", "dsy", "lensx", "lensy")]
+    a, b = o.create_rays(*arrs), r.create_rays(*arrs)
+    first = a["tries"] == 0
+    assert first.mean() > 0.2  # optical vignetting rejects many first tries
+    for k in orc.RAY_OUT_FIELDS:
+        np.testing.assert_array_equal(a[k][:, first], b[k][:, first], err_msg=k)
+
+
+@pytest.mark.parametrize("kw", TL_CASES)
+def test_thinlens_filter_pixel_and_imager(kw):
+    img = workloads.disc_bokeh_image(64) if kw.get("bokeh_enable_image") else None
+    kw = dict(kw)
+    kw.setdefault("fstop", 1.4)
+    kw.setdefault("focus_dist", 35.0)
+    p = _tl_params(bidir_sample_mult=6, **kw)
+    o, r = orc.OracleCamera(p, img), ref.RefCamera(p, img)
+    W, H, spp = 128, 72, 9
+    z = 0.75 if kw.get("units") == abi.LB_UNITS_M else 75.0
+    fr = workloads.highlight_frame(W, H, spp, o.state.tan_fov, "cpu", z_plane=z, pitch=z * 0.072, radius=z * 0.0018, n_extra_aov=1)
+    aovs = [("RGBA", 0, 1), ("light0", 0, 0), ("N", 1, 0)]
+    vals = [None, fr["aov_values"][0].numpy(), fr["aov_values"][0].numpy()]
+    args = (fr["px"].numpy(), fr["py"].numpy(), fr["rgba"].numpy(), fr["pos_cs"].numpy(), 1.0 / spp)
+    o.filter_begin(W, H, aovs)
+    o.filter_accumulate(*args, aov_values=vals)
+    r.filter_begin(W, H, aovs, spp=spp)
+    r.filter_accumulate(*args, aov_values=vals)
+    st = o.filter_stats()
+    assert st["redistributed"] > 50 and st["splats"] > 500, st
+    for a in range(len(aovs)):
+        bo, wo = o.buffers(a)
+        br, wr = r.buffers(a)
+        np.testing.assert_array_equal(bo, br, err_msg=f"buffer of {aovs[a][0]}")
+        np.testing.assert_array_equal(wo, wr)
+        np.testing.assert_array_equal(o.resolve(a), r.resolve(a))
