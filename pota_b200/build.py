@@ -17,9 +17,9 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-GEN = os.path.join(CSRC, "gen")
-OBJ = os.path.join(CSRC, "build")
-LIB = os.path.join(HERE, "liblentil_b200.so")
+GEN = os.path.join(CSRC, "gen" + os.environ.get("LB_BUILD_TAG", ""))
+OBJ = os.path.join(CSRC, "build" + os.environ.get("LB_BUILD_TAG", ""))
+LIB = os.environ.get("LB_LIB_OUT") or os.path.join(HERE, "liblentil_b200.so")  # LB_LIB_OUT: tuning variants
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden", "-I", CSRC]
@@ -88,7 +88,7 @@ def build(force: bool = False, unrolled: bool = True, verbose: bool = False, job
     units = {os.path.join(CSRC, k): v for k, v in UNITS.items()}
     if gen_units:
         for g in gen_units:
-            units[g] = ["-DLB_HAVE_UNROLLED"]
+            units[g] = ["-DLB_HAVE_UNROLLED", *os.environ.get("LB_EXTRA_NVCC_FLAGS", "").split()]
     else:
         units[os.path.join(CSRC, "unrolled_none.cu")] = []
     todo, objs = [], []

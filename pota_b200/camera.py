@@ -17,7 +17,7 @@ import numpy as np
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "liblentil_b200.so")
+_LIB_PATH = os.environ.get("LB_LIBRARY") or os.path.join(_HERE, "liblentil_b200.so")  # LB_LIBRARY: tuning variants
 _lib = None
 
 RAY_OUT_FIELDS = ("origin", "dir", "dOdx", "dOdy", "dDdx", "dDdy", "weight")
