@@ -181,7 +181,11 @@ LB_API int lb_bench_red_peak(int device, int megabytes, double *gbytes_per_s_out
 
 /* ---- filter / imager ---------------------------------------------------------------------- */
 
-enum { LB_FILTER_GAUSSIAN = 0, LB_FILTER_CLOSEST = 1 }; /* AOVData::original_filter, lentil.h:827,832 */
+/* AOVData::original_filter (lentil.h:827,832); LB_FILTER_CRYPTO marks an AOVData with is_crypto set
+ * (lentil.h:1036-1038): a ranked cryptomatte AOV ("crypto_material00", ...), accumulated as per-pixel
+ * {hash id -> weight} tables (aov_data.h:126-128) and resolved by rank (lentil_imager.cpp:122-161). */
+enum { LB_FILTER_GAUSSIAN = 0, LB_FILTER_CLOSEST = 1, LB_FILTER_CRYPTO = 2 };
+enum { LB_CRYPTO_MAX_DEPTH = 8, LB_CRYPTO_DEFAULT_SLOTS = 16, LB_CRYPTO_MAX_SLOTS = 64 };
 enum { LB_AOV_PLAIN = 0, LB_AOV_RGBA = 1, LB_AOV_LENTIL_DEBUG = 2 }; /* atstring_rgba / atstring_lentil_debug */
 
 typedef struct lb_aov_desc {
@@ -196,6 +200,9 @@ typedef struct lb_frame_desc {
   int32_t xres, yres;
   int32_t xres_without_region, yres_without_region;
   int32_t region_min_x, region_min_y;
+  int32_t crypto_slots; /* distinct ids kept per pixel and cryptomatte AOV (the reference's std::map is unbounded);
+                           0 = LB_CRYPTO_DEFAULT_SLOTS.  Contributions that find every slot taken are counted in
+                           lb_filter_stats.crypto_dropped. */
 } lb_frame_desc;
 
 /* One batch of AOV samples, as filter_pixel reads them from the AtAOVSampleIterator
@@ -211,6 +218,13 @@ typedef struct lb_samples {
   const float *const *aov_values; /* [n_aov] device pointers to [n][4] values already widened to RGBA (:206-234);
                                      entry may be NULL for the RGBA role (uses `rgba`) and for lentil_debug */
   float inv_density;        /* inverse_sample_density (:84) */
+  /* cryptomatte depth sub-samples, what cryptomatte_construct_cache (lentil.h:779-811) walks with
+   * AiAOVSampleIteratorGetNextDepth; all NULL / 0 when the frame has no LB_FILTER_CRYPTO AOV */
+  int32_t crypto_depth;           /* D <= LB_CRYPTO_MAX_DEPTH: sub-sample slots stored per sample */
+  const uint8_t *crypto_count;    /* [n] valid sub-samples of each sample (<= D); NULL = D for every sample */
+  const float *crypto_opacity;    /* [n][D] AiColorToGrey(opacity AOV) of each sub-sample (:790) */
+  const float *const *crypto_ids; /* [n_aov] device pointers to [n][D] hash ids of that AOV (:791); NULL entries for
+                                     the other AOVs */
 } lb_samples;
 enum { LB_SAMPLE_VOLUME = 1u, LB_SAMPLE_IGNORE = 2u }; /* volume_in_sample (:136), lentil_bidir_ignore > 0 (:162) */
 
@@ -220,6 +234,7 @@ typedef struct lb_filter_stats {
   uint64_t splats;        /* successful (source, lens sample) pairs that reached add_to_buffer */
   uint64_t attempts;      /* reverse-trace attempts (total_samples_taken summed) */
   uint64_t passthrough;   /* filter_and_add_to_buffer_new adds (:243-246) */
+  uint64_t crypto_dropped;/* cryptomatte contributions lost because a pixel already held crypto_slots other ids */
 } lb_filter_stats;
 
 /* setup_filter (lentil.h:1056-1117): allocates zeroed device framebuffers. */
@@ -231,14 +246,23 @@ LB_API int lb_filter_accumulate_host(lb_camera *cam, const lb_samples *samples);
 LB_API int lb_filter_get_stats(lb_camera *cam, lb_filter_stats *out); /* synchronises */
 /* Diagnostic: lt_sample_aperture Newton iterations executed since lb_filter_begin (synchronises). */
 LB_API int lb_filter_newton_iterations(lb_camera *cam, uint64_t *out);
-/* driver_process_bucket (lentil_imager.cpp:112-189) for one bucket of one AOV -> rgba_out [h][w][4]. */
+/* driver_process_bucket (lentil_imager.cpp:112-189) for one bucket of one AOV -> rgba_out [h][w][4].
+ * Cryptomatte AOVs: rank 0 / 2 / 4 from the AOV name as there (:124-126); rgba_out = {id, coverage, id, coverage}
+ * of ranks r and r+1.  As in the reference (:132-134, a `break` out of the row loop), the first pixel of a
+ * bucket row that holds <= rank ids ends that row: it and the pixels after it are left as the caller
+ * supplied them, so rgba_out is read-modify-write for these AOVs. */
 LB_API int lb_imager_resolve(lb_camera *cam, int aov, int x0, int y0, int w, int h, float *rgba_out, lb_stream stream);
 LB_API int lb_imager_resolve_host(lb_camera *cam, int aov, int x0, int y0, int w, int h, float *rgba_out);
 /* Raw accumulators (device pointers owned by the camera): AOVData::buffer [yres][xres][4],
- * filter_weight_buffer [yres][xres]. */
+ * filter_weight_buffer [yres][xres].  For a cryptomatte AOV the plane's x component is
+ * AOVData::crypto_total_weight (aov_data.h:128), y/z/w are unused. */
 LB_API int lb_filter_buffers(lb_camera *cam, int aov, float **buffer, float **filter_weight_buffer);
 /* Copies of the raw accumulators in HOST memory (either pointer may be NULL); synchronises. */
 LB_API int lb_filter_buffers_host(lb_camera *cam, int aov, float *buffer_out, float *filter_weight_buffer_out);
+/* AOVData::crypto_hash_map of a cryptomatte AOV as fixed-size tables in HOST memory: ids_out and
+ * weights_out are [yres][xres][crypto_slots]; unused slots have id NaN (bits 0xFFFFFFFF) and weight 0.
+ * Returns the slot count through *slots_out (any pointer may be NULL); synchronises. */
+LB_API int lb_filter_crypto_host(lb_camera *cam, int aov, float *ids_out, float *weights_out, int *slots_out);
 
 /* ---- multi-GPU (new: the reference is single-process) -------------------------------------- */
 

@@ -24,6 +24,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
 #include <thread>
 #include <vector>
@@ -398,7 +399,8 @@ struct AOV {
   std::string name;
   int filter = LB_FILTER_GAUSSIAN;
   int role = LB_AOV_PLAIN;
-  std::vector<float> buffer;  // RGBA, AOVData::buffer (aov_data.h:114-164)
+  std::vector<float> buffer;  // RGBA, AOVData::buffer (aov_data.h:114-164); crypto AOVs: x = crypto_total_weight (:128)
+  std::vector<std::map<float, float>> crypto_hash_map;  // aov_data.h:127
 };
 
 struct orc_camera {
@@ -407,6 +409,7 @@ struct orc_camera {
   ImageData image;
   std::vector<float> zbuffer, zbuffer_debug, filter_weight_buffer;
   std::vector<AOV> aovs;
+  bool has_crypto = false;  // cryptomatte_lentil, lentil.h:193
   double lens_outer_pupil_radius = 0, lens_inner_pupil_radius = 0, lens_length = 0, lens_back_focal_length = 0;
   double lens_effective_focal_length = 0, lens_aperture_pos = 0, lens_aperture_housing_radius = 0;
   double lens_inner_pupil_curvature_radius = 0, lens_outer_pupil_curvature_radius = 0, lens_field_of_view = 0;
@@ -880,12 +883,45 @@ struct orc_camera {
     }
   }
 
+  // cryptomatte_construct_cache, lentil.h:779-811: the depth sub-samples of sample i replace the
+  // AiAOVSampleIteratorGetNextDepth walk
+  void cryptomatte_construct_cache(std::vector<std::map<float, float>> &crypto_hashmap_cache, const lb_samples *S, size_t i) {
+    for (size_t a = 0; a < aovs.size(); ++a) {
+      if (aovs[a].filter != LB_FILTER_CRYPTO) continue;
+      float iterative_transparency_weight = 1.0f;
+      float quota = 1.0;
+      float sample_value = 0.0f;
+      const int D = S->crypto_depth;
+      const float *ids = (S->crypto_ids && S->crypto_ids[a]) ? S->crypto_ids[a] + (size_t)D * i : nullptr;
+      const int count = !ids ? 0 : (S->crypto_count ? std::min<int>(S->crypto_count[i], D) : D);
+      for (int d = 0; d < count; ++d) {
+        const float sub_sample_opacity = S->crypto_opacity ? S->crypto_opacity[(size_t)D * i + d] : 0.0f;
+        sample_value = ids[d];
+        const float sub_sample_weight = sub_sample_opacity * iterative_transparency_weight;
+        iterative_transparency_weight *= (1.0f - sub_sample_opacity);
+        quota -= sub_sample_weight;
+        crypto_hashmap_cache[a][sample_value] += sub_sample_weight;
+      }
+      if (quota > 0.0) crypto_hashmap_cache[a][sample_value] += quota;
+    }
+  }
+
+  // lentil.h:814-819
+  void add_to_buffer_cryptomatte(AOV &aov, int px, std::map<float, float> &cryptomatte_cache, const float sample_weight) {
+    aov.buffer[4 * (size_t)px] += sample_weight;  // crypto_total_weight
+    for (auto const &sample : cryptomatte_cache) aov.crypto_hash_map[px][sample.first] += sample.second * sample_weight;
+  }
+
   // lentil.h:938-955
-  void filter_and_add_to_buffer_new(int px, int py, float depth, const std::vector<float> &aov_values, float inv_density) {
+  void filter_and_add_to_buffer_new(int px, int py, float depth, std::vector<std::map<float, float>> &crypto_cache,
+                                    const std::vector<float> &aov_values, float inv_density) {
     const unsigned pixelnumber = xres * py + px;
     float filter_weight = 1.0;
     const float white[3] = {1, 1, 1};
-    for (size_t a = 0; a < aovs.size(); ++a) add_to_buffer(aovs[a], pixelnumber, &aov_values[4 * a], 0.0, depth, filter_weight * inv_density, white);
+    for (size_t a = 0; a < aovs.size(); ++a) {
+      if (aovs[a].filter == LB_FILTER_CRYPTO) add_to_buffer_cryptomatte(aovs[a], pixelnumber, crypto_cache[a], inv_density);
+      else add_to_buffer(aovs[a], pixelnumber, &aov_values[4 * a], 0.0, depth, filter_weight * inv_density, white);
+    }
   }
 
   // lentil_filter.cpp:105-301 for ONE sample of the iterator (PolynomialOptics branch)
@@ -923,6 +959,8 @@ struct orc_camera {
     }
     const float sample_luminance = (sample[0] + sample[1] + sample[2]) / 3.0;
     if (flags & LB_SAMPLE_IGNORE) redistribute = false;  // :162-164
+    std::vector<std::map<float, float>> crypto_cache(aovs.size());  // :167-169
+    if (has_crypto) cryptomatte_construct_cache(crypto_cache, S, i);
     float fitted_bidir_add_energy = 0.0;
     if (bidir_add_energy > 0.0) fitted_bidir_add_energy = additional_luminance_soft_trans(sample_luminance);
     float luminance_mult = std::max(0.0, std::pow(std::min(sample_luminance, 20.0f), 0.5) * bidir_sample_mult);  // :177
@@ -938,6 +976,7 @@ struct orc_camera {
     // :206-234
     std::vector<float> aov_values(4 * aovs.size(), 0.0f);
     for (size_t a = 0; a < aovs.size(); ++a) {
+      if (aovs[a].filter == LB_FILTER_CRYPTO) continue;  // :208
       if (aovs[a].role == LB_AOV_LENTIL_DEBUG) {
         float v = samples * redistribute;
         aov_values[4 * a] = aov_values[4 * a + 1] = aov_values[4 * a + 2] = aov_values[4 * a + 3] = v;  // AtRGBA = float
@@ -949,7 +988,7 @@ struct orc_camera {
     ++stats.samples;
     if (cameraType == LB_CAMERA_POLYNOMIAL_OPTICS && std::abs(csp[2]) < (lens_length * 0.1)) redistribute = false;  // :240 (PO case only)
     if (redistribute == false) {
-      filter_and_add_to_buffer_new(px, py, depth, aov_values, inverse_sample_density);
+      filter_and_add_to_buffer_new(px, py, depth, crypto_cache, aov_values, inverse_sample_density);
       ++stats.passthrough;
       return;
     }
@@ -1017,8 +1056,10 @@ struct orc_camera {
         if ((pixel_x >= xres_d) || (pixel_x < 0) || (pixel_y >= yres_d) || (pixel_y < 0)) { --count; continue; }
         unsigned pixelnumber = (unsigned)((int)std::floor(pixel_x) + ((int)std::floor(pixel_y) * xres));
         float filter_weight = 1.0;
-        for (size_t a = 0; a < aovs.size(); ++a)
-          add_to_buffer(aovs[a], pixelnumber, &aov_values[4 * a], fitted_bidir_add_energy, depth, filter_weight * inverse_sample_density * inv_samples, rgb_weight);
+        for (size_t a = 0; a < aovs.size(); ++a) {
+          if (aovs[a].filter == LB_FILTER_CRYPTO) add_to_buffer_cryptomatte(aovs[a], pixelnumber, crypto_cache[a], inverse_sample_density * inv_samples);
+          else add_to_buffer(aovs[a], pixelnumber, &aov_values[4 * a], fitted_bidir_add_energy, depth, filter_weight * inverse_sample_density * inv_samples, rgb_weight);
+        }
         ++stats.splats;
       }
       return;
@@ -1042,8 +1083,10 @@ struct orc_camera {
         if ((pixel.x >= xres_d) || (pixel.x < 0) || (pixel.y >= yres_d) || (pixel.y < 0) || (pixel.x != pixel.x) || (pixel.y != pixel.y)) { --count; continue; }
         unsigned pixelnumber = (unsigned)((int)std::floor(pixel.x) + ((int)std::floor(pixel.y) * xres));
         float filter_weight = 1.0;
-        for (size_t a = 0; a < aovs.size(); ++a)
-          add_to_buffer(aovs[a], pixelnumber, &aov_values[4 * a], fitted_bidir_add_energy, depth, filter_weight * inverse_sample_density * inv_samples, rgb_weight);
+        for (size_t a = 0; a < aovs.size(); ++a) {
+          if (aovs[a].filter == LB_FILTER_CRYPTO) add_to_buffer_cryptomatte(aovs[a], pixelnumber, crypto_cache[a], inverse_sample_density * inv_samples);
+          else add_to_buffer(aovs[a], pixelnumber, &aov_values[4 * a], fitted_bidir_add_energy, depth, filter_weight * inverse_sample_density * inv_samples, rgb_weight);
+        }
         ++stats.splats;
       }
     }
@@ -1273,10 +1316,12 @@ int orc_filter_begin(orc_camera *c, const lb_frame_desc *f, int n_aov, const lb_
   c->zbuffer_debug.assign(npx, 0.0f);
   c->filter_weight_buffer.assign(npx, 0.0f);
   c->aovs.clear();
+  c->has_crypto = false;
   for (int a = 0; a < n_aov; ++a) {
     AOV v;
     v.name = aovs[a].name; v.filter = aovs[a].filter; v.role = aovs[a].role;
     v.buffer.assign(4 * npx, 0.0f);
+    if (v.filter == LB_FILTER_CRYPTO) { v.crypto_hash_map.assign(npx, {}); c->has_crypto = true; }  // aov_data.h:145-150
     c->aovs.push_back(std::move(v));
   }
   c->stats = lb_filter_stats{};
@@ -1295,7 +1340,7 @@ int orc_filter_accumulate(orc_camera *cam, const lb_samples *S, int nthreads) {
   std::vector<orc_camera> clones(nthreads, *cam);
   for (auto &c : clones) {
     std::fill(c.filter_weight_buffer.begin(), c.filter_weight_buffer.end(), 0.0f);
-    for (auto &a : c.aovs) std::fill(a.buffer.begin(), a.buffer.end(), 0.0f);
+    for (auto &a : c.aovs) { std::fill(a.buffer.begin(), a.buffer.end(), 0.0f); for (auto &m : a.crypto_hash_map) m.clear(); }
     c.stats = lb_filter_stats{};
     c.bw_newton_its = c.bw_attempts = 0;
   }
@@ -1307,6 +1352,9 @@ int orc_filter_accumulate(orc_camera *cam, const lb_samples *S, int nthreads) {
     for (size_t i = 0; i < cam->filter_weight_buffer.size(); ++i) cam->filter_weight_buffer[i] += c.filter_weight_buffer[i];
     for (size_t a = 0; a < cam->aovs.size(); ++a)
       for (size_t i = 0; i < cam->aovs[a].buffer.size(); ++i) cam->aovs[a].buffer[i] += c.aovs[a].buffer[i];
+    for (size_t a = 0; a < cam->aovs.size(); ++a)
+      for (size_t i = 0; i < cam->aovs[a].crypto_hash_map.size(); ++i)
+        for (auto const &kv : c.aovs[a].crypto_hash_map[i]) cam->aovs[a].crypto_hash_map[i][kv.first] += kv.second;
     cam->stats.samples += c.stats.samples; cam->stats.redistributed += c.stats.redistributed; cam->stats.splats += c.stats.splats;
     cam->stats.attempts += c.stats.attempts; cam->stats.passthrough += c.stats.passthrough;
     cam->bw_newton_its += c.bw_newton_its; cam->bw_attempts += c.bw_attempts;
@@ -1316,7 +1364,7 @@ int orc_filter_accumulate(orc_camera *cam, const lb_samples *S, int nthreads) {
 
 int orc_filter_get_stats(orc_camera *c, lb_filter_stats *out) { if (!c || !out) return LB_ERR_INVALID; *out = c->stats; return LB_OK; }
 
-// driver_process_bucket, lentil_imager.cpp:112-189 (non-crypto branch)
+// driver_process_bucket, lentil_imager.cpp:112-189
 int orc_imager_resolve(orc_camera *c, int aov, int x0, int y0, int w, int h, float *rgba_out) {
   if (!c || aov < 0 || aov >= (int)c->aovs.size() || !rgba_out) return LB_ERR_INVALID;
   const AOV &A = c->aovs[aov];
@@ -1325,6 +1373,26 @@ int orc_imager_resolve(orc_camera *c, int aov, int x0, int y0, int w, int h, flo
       int y = j + y0, x = i + x0;
       int in_idx = j * w + i;
       int linear_pixel = (x - c->region_min_x) + ((y - c->region_min_y) * (int)c->xres);
+      if (A.name.find("crypto") != std::string::npos) {  // :122-161
+        int rank = 0;
+        if (A.name == "crypto_material01" || A.name == "crypto_asset01" || A.name == "crypto_object01") rank = 2;
+        else if (A.name == "crypto_material02" || A.name == "crypto_asset02" || A.name == "crypto_object02") rank = 4;
+        if (A.crypto_hash_map.empty()) return LB_ERR_INVALID;
+        const std::map<float, float> &m = A.crypto_hash_map[linear_pixel];
+        if ((int)m.size() <= rank) break;  // :132-134 leaves the rest of this bucket row untouched
+        std::vector<std::pair<float, float>> all_vals(m.begin(), m.end());
+        std::sort(all_vals.begin(), all_vals.end(), [](const std::pair<float, float> x, const std::pair<float, float> y) { return x.second > y.second; });
+        float out[4] = {0, 0, 0, 0};
+        int iter = 0;
+        const float total = A.buffer[4 * (size_t)linear_pixel];
+        for (auto const &v : all_vals) {
+          if (iter == rank) { out[0] = v.first; out[1] = v.second / total; }
+          else if (iter == rank + 1) { out[2] = v.first; out[3] = v.second / total; }
+          iter++;
+        }
+        for (int k = 0; k < 4; ++k) rgba_out[4 * (size_t)in_idx + k] = out[k];
+        continue;
+      }
       float image[4] = {A.buffer[4 * (size_t)linear_pixel], A.buffer[4 * (size_t)linear_pixel + 1], A.buffer[4 * (size_t)linear_pixel + 2], A.buffer[4 * (size_t)linear_pixel + 3]};
       if (A.filter == LB_FILTER_GAUSSIAN) {
         if (A.role != LB_AOV_LENTIL_DEBUG) {
@@ -1340,6 +1408,30 @@ int orc_imager_resolve(orc_camera *c, int aov, int x0, int y0, int w, int h, flo
       for (int k = 0; k < 4; ++k) rgba_out[4 * (size_t)in_idx + k] = image[k];
     }
   return LB_OK;
+}
+
+// AOVData::crypto_hash_map as fixed-size tables, ascending id per pixel; unused slots id NaN (all bits set), weight 0.
+// Returns the largest map size found (may exceed `slots`: such pixels are truncated).
+int orc_filter_crypto(orc_camera *c, int aov, int slots, float *ids_out, float *weights_out, float *total_out) {
+  if (!c || aov < 0 || aov >= (int)c->aovs.size() || c->aovs[aov].crypto_hash_map.empty()) return -1;
+  const AOV &A = c->aovs[aov];
+  size_t mx = 0;
+  for (size_t p = 0; p < A.crypto_hash_map.size(); ++p) {
+    mx = std::max(mx, A.crypto_hash_map[p].size());
+    if (total_out) total_out[p] = A.buffer[4 * p];
+    int k = 0;
+    for (auto const &kv : A.crypto_hash_map[p]) {
+      if (k >= slots) break;
+      if (ids_out) ids_out[p * slots + k] = kv.first;
+      if (weights_out) weights_out[p * slots + k] = kv.second;
+      ++k;
+    }
+    for (; k < slots; ++k) {
+      if (ids_out) { const uint32_t nanbits = 0xFFFFFFFFu; memcpy(&ids_out[p * slots + k], &nanbits, 4); }
+      if (weights_out) weights_out[p * slots + k] = 0.0f;
+    }
+  }
+  return (int)mx;
 }
 
 int orc_filter_buffers(orc_camera *c, int aov, float **buffer, float **weight) {

@@ -17,6 +17,7 @@ int orc_filter_accumulate(orc_camera *cam, const lb_samples *S, int nthreads);
 int orc_filter_get_stats(orc_camera *c, lb_filter_stats *out);
 int orc_imager_resolve(orc_camera *c, int aov, int x0, int y0, int w, int h, float *rgba_out);
 int orc_filter_buffers(orc_camera *c, int aov, float **buffer, float **weight);
+int orc_filter_crypto(orc_camera *c, int aov, int slots, float *ids_out, float *weights_out, float *total_out);
 void orc_camera_counters(const orc_camera *c, uint64_t out[4]);
 #ifdef __cplusplus
 }

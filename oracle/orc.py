@@ -39,6 +39,7 @@ def lib():
         L.orc_filter_get_stats.argtypes = [C.c_void_p, C.POINTER(abi.FilterStats)]
         L.orc_imager_resolve.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.orc_filter_buffers.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+        L.orc_filter_crypto.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_camera_counters.argtypes = [C.c_void_p, C.POINTER(C.c_uint64 * 4)]
         L.orc_tea8.restype = C.c_uint
         L.orc_tea8.argtypes = [C.c_uint, C.c_uint]
@@ -140,21 +141,8 @@ class OracleCamera:
         rc = lib().orc_filter_begin(self._h, C.byref(self._frame), len(aovs), arr)
         assert rc == 0, rc
 
-    def filter_accumulate(self, px, py, rgba, pos_cs, inv_density, aov_values=None, raydir=None, transmission=None, flags=None, nthreads=1):
-        n = px.shape[0]
-        keep = [np.ascontiguousarray(px, np.int32), np.ascontiguousarray(py, np.int32), np.ascontiguousarray(rgba, np.float32), np.ascontiguousarray(pos_cs, np.float32)]
-        opt = [None if a is None else np.ascontiguousarray(a, dt) for a, dt in ((raydir, np.float32), (transmission, np.float32), (flags, np.uint32))]
-        av = (C.c_void_p * max(self._naov, 1))()
-        keep_av = []
-        for i in range(self._naov):
-            a = None if aov_values is None else aov_values[i]
-            if a is not None:
-                a = np.ascontiguousarray(a, np.float32)
-                keep_av.append(a)
-                av[i] = a.ctypes.data
-            else:
-                av[i] = None
-        S = abi.Samples(n, _ptr(keep[0]), _ptr(keep[1]), _ptr(keep[2]), _ptr(keep[3]), _ptr(opt[0]), _ptr(opt[1]), _ptr(opt[2]), av, inv_density)
+    def filter_accumulate(self, px, py, rgba, pos_cs, inv_density, aov_values=None, raydir=None, transmission=None, flags=None, nthreads=1, crypto=None):
+        S, _keep = abi.host_samples(self._naov, px, py, rgba, pos_cs, inv_density, aov_values, raydir, transmission, flags, crypto)
         rc = lib().orc_filter_accumulate(self._h, C.byref(S), nthreads)
         assert rc == 0, rc
 
@@ -163,16 +151,30 @@ class OracleCamera:
         lib().orc_filter_get_stats(self._h, C.byref(s))
         return {k: getattr(s, k) for k, _ in s._fields_}
 
-    def resolve(self, aov, x0=None, y0=None, w=None, h=None):
+    _resolve_fn = "orc_imager_resolve"
+    _crypto_fn = "orc_filter_crypto"
+
+    def resolve(self, aov, x0=None, y0=None, w=None, h=None, fill=0.0):
+        """fill: what the bucket holds beforehand (cryptomatte rows can end early and leave it, lentil_imager.cpp:132-134)."""
         f = self._frame
         x0 = f.region_min_x if x0 is None else x0
         y0 = f.region_min_y if y0 is None else y0
         w = f.xres if w is None else w
         h = f.yres if h is None else h
-        out = np.zeros((h, w, 4), np.float32)
-        rc = lib().orc_imager_resolve(self._h, aov, x0, y0, w, h, _ptr(out))
+        out = np.full((h, w, 4), fill, np.float32)
+        rc = getattr(lib(), self._resolve_fn)(self._h, aov, x0, y0, w, h, _ptr(out))
         assert rc == 0, rc
         return out
+
+    def crypto(self, aov, slots=16):
+        """(ids [yres][xres][slots], weights, total_weight [yres][xres], largest map size)."""
+        f = self._frame
+        ids = np.zeros((f.yres, f.xres, slots), np.float32)
+        wts = np.zeros((f.yres, f.xres, slots), np.float32)
+        tot = np.zeros((f.yres, f.xres), np.float32)
+        mx = getattr(lib(), self._crypto_fn)(self._h, aov, slots, _ptr(ids), _ptr(wts), _ptr(tot))
+        assert mx >= 0, mx
+        return ids, wts, tot, mx
 
     def buffers(self, aov):
         b, w = C.c_void_p(), C.c_void_p()

@@ -42,6 +42,7 @@ def lib():
         L.ref_filter_accumulate.argtypes = [vp, C.POINTER(abi.Samples), C.c_int]
         L.ref_imager_resolve.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]
         L.ref_filter_buffers.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(vp)]
+        L.ref_filter_crypto.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp]
         L.ref_tea8.restype = C.c_uint
         L.ref_tea8.argtypes = [C.c_uint, C.c_uint]
         L.ref_rng.restype = C.c_float
@@ -120,35 +121,33 @@ class RefCamera(orc.OracleCamera):
         rc = lib().ref_filter_begin(self._h, C.byref(self._frame), len(aovs), arr, aa)
         assert rc == 0, rc
 
-    def filter_accumulate(self, px, py, rgba, pos_cs, inv_density, aov_values=None, raydir=None, transmission=None, flags=None, nthreads=1):
-        n = px.shape[0]
-        keep = [np.ascontiguousarray(px, np.int32), np.ascontiguousarray(py, np.int32), np.ascontiguousarray(rgba, np.float32), np.ascontiguousarray(pos_cs, np.float32)]
-        opt = [None if a is None else np.ascontiguousarray(a, dt) for a, dt in ((raydir, np.float32), (transmission, np.float32), (flags, np.uint32))]
-        av = (C.c_void_p * max(self._naov, 1))()
-        keep_av = []
-        for i in range(self._naov):
-            a = None if aov_values is None else aov_values[i]
-            if a is not None:
-                a = np.ascontiguousarray(a, np.float32)
-                keep_av.append(a)
-                av[i] = a.ctypes.data
-        S = abi.Samples(n, orc._ptr(keep[0]), orc._ptr(keep[1]), orc._ptr(keep[2]), orc._ptr(keep[3]), orc._ptr(opt[0]), orc._ptr(opt[1]), orc._ptr(opt[2]), av, inv_density)
+    def filter_accumulate(self, px, py, rgba, pos_cs, inv_density, aov_values=None, raydir=None, transmission=None, flags=None, nthreads=1, crypto=None):
+        S, _keep = abi.host_samples(self._naov, px, py, rgba, pos_cs, inv_density, aov_values, raydir, transmission, flags, crypto)
         rc = lib().ref_filter_accumulate(self._h, C.byref(S), nthreads)
         assert rc == 0, rc
 
     def filter_stats(self):
         raise NotImplementedError("the reference keeps no counters")
 
-    def resolve(self, aov, x0=None, y0=None, w=None, h=None):
+    def resolve(self, aov, x0=None, y0=None, w=None, h=None, fill=0.0):
         f = self._frame
         x0 = f.region_min_x if x0 is None else x0
         y0 = f.region_min_y if y0 is None else y0
         w = f.xres if w is None else w
         h = f.yres if h is None else h
-        out = np.zeros((h, w, 4), np.float32)
+        out = np.full((h, w, 4), fill, np.float32)
         rc = lib().ref_imager_resolve(self._h, aov, x0, y0, w, h, orc._ptr(out))
         assert rc == 0, rc
         return out
+
+    def crypto(self, aov, slots=16):
+        f = self._frame
+        ids = np.zeros((f.yres, f.xres, slots), np.float32)
+        wts = np.zeros((f.yres, f.xres, slots), np.float32)
+        tot = np.zeros((f.yres, f.xres), np.float32)
+        mx = lib().ref_filter_crypto(self._h, aov, slots, orc._ptr(ids), orc._ptr(wts), orc._ptr(tot))
+        assert mx >= 0, mx
+        return ids, wts, tot, mx
 
     def buffers(self, aov):
         b, w = C.c_void_p(), C.c_void_p()

@@ -28,7 +28,9 @@ extern const AtNodeMethods *LentilImagerMtd;       // lentil_imager.cpp:7
 
 struct ref_camera {
   AtUniverse uni;
-  AtNode options, camera, filter, imager, op;
+  AtNode options, camera, filter, imager, op, crypto, exr;
+  CryptomatteData cryptodata;
+  AtArray aov_shaders, outputs;
   OperatorData opdata;
   Camera *cam = nullptr;
   std::vector<lb_aov_desc> aovs;
@@ -79,10 +81,11 @@ void apply_params(ref_camera *r, const lb_camera_params *p) {  // names: lentil_
 void build_operator_aovs(ref_camera *r) {
   r->opdata.aovs.clear();
   for (size_t i = 0; i < r->aovs.size(); ++i) {
+    if (r->aovs[i].filter == LB_FILTER_CRYPTO) continue;  // those arrive through options.outputs (setup_crypto_aovs, lentil.h:1015-1052)
     std::string out = std::string(r->aovs[i].name) + " RGBA lentil_replaced_filter shim_driver";
     AOVData a(&r->uni, out);
     a.original_filter = AtString(r->aovs[i].filter == LB_FILTER_CLOSEST ? "closest_filter" : "gaussian_filter");
-    a.index = (int)i;
+    a.index = (int)r->opdata.aovs.size();
     r->opdata.aovs.push_back(a);
   }
   r->opdata.aovcount = (int)r->opdata.aovs.size();
@@ -104,6 +107,15 @@ void update_camera(ref_camera *r) {
   set_b(o, "enable_progressive_render", false);
   set_f(o, "meters_per_unit", 0.01f);
   build_operator_aovs(r);
+  // cryptomatte: a `cryptomatte` AOV shader whose setup has completed (lentil.h:244-270) and ranked crypto outputs
+  // written by an EXR driver (lentil.h:1104-1114)
+  r->aov_shaders.ptrs.clear();
+  r->outputs.strs.clear();
+  for (auto &a : r->aovs)
+    if (a.filter == LB_FILTER_CRYPTO) r->outputs.strs.push_back(std::string(a.name) + " FLOAT cryptomatte_filter shim_exr");
+  if (!r->outputs.strs.empty()) r->aov_shaders.ptrs.push_back(&r->crypto);
+  AiNodeSetArray(&o, AtString("aov_shaders"), &r->aov_shaders);
+  AiNodeSetArray(&o, AtString("outputs"), &r->outputs);
   lentilMethods->Update(&r->uni.session, &r->camera);
   r->cam = (Camera *)AiNodeGetLocalData(&r->camera);
 }
@@ -115,7 +127,9 @@ int ref_camera_create(const lb_camera_params *p, const lb_bokeh_image *img, ref_
   ref_camera *r = new ref_camera();
   r->uni.options = &r->options;
   r->uni.camera = &r->camera;
-  r->uni.nodes = {&r->options, &r->camera, &r->filter, &r->imager, &r->op};
+  r->uni.nodes = {&r->options, &r->camera, &r->filter, &r->imager, &r->op, &r->crypto, &r->exr};
+  r->crypto.name = "cryptomatte_shader"; r->crypto.entry.name = "cryptomatte"; r->crypto.local_data = &r->cryptodata;
+  r->exr.name = "shim_exr"; r->exr.entry.name = "driver_exr";
   r->uni.entry_counts["imager_denoiser_oidn"] = 1;  // -> filter_width 1.0 (lentil.h:1083-1088): no footprint overlap
   for (AtNode *n : r->uni.nodes) n->universe = &r->uni;
   r->options.name = "options"; r->options.entry.name = "options";
@@ -233,9 +247,16 @@ int ref_filter_accumulate(ref_camera *r, const lb_samples *S, int nthreads) {
   it.aovs["lentil_raydir"] = {S->raydir ? S->raydir : zero.data(), 3};
   it.aovs["transmission"] = {S->transmission ? S->transmission : zero.data(), 4};
   for (size_t a = 0; a < r->aovs.size(); ++a) {
+    if (r->aovs[a].filter == LB_FILTER_CRYPTO) {
+      it.depth_ids[r->aovs[a].name] = (S->crypto_ids && S->crypto_ids[a]) ? S->crypto_ids[a] : nullptr;
+      continue;
+    }
     const float *v = (S->aov_values && S->aov_values[a]) ? S->aov_values[a] : S->rgba;
     it.aovs[r->aovs[a].name] = {v, 4};
   }
+  it.depth_n = S->crypto_depth;
+  it.depth_count = S->crypto_count;
+  it.depth_opacity = S->crypto_opacity;
   // runs of consecutive samples sharing a pixel
   std::vector<std::pair<size_t, size_t>> runs;
   for (size_t b = 0; b < n;) {
@@ -273,12 +294,41 @@ int ref_imager_resolve(ref_camera *r, int aov, int x0, int y0, int w, int h, flo
   return LB_OK;
 }
 
+static AOVData *find_aov(ref_camera *r, int aov) {
+  if (aov < 0 || aov >= (int)r->aovs.size()) return nullptr;
+  for (auto &a : r->cam->aovs) if (a.name == AtString(r->aovs[aov].name)) return &a;
+  return nullptr;
+}
+
 int ref_filter_buffers(ref_camera *r, int aov, float **buffer, float **weight) {
-  Camera *c = r->cam;
-  if (aov < 0 || aov >= (int)c->aovs.size()) return LB_ERR_INVALID;
-  if (buffer) *buffer = &c->aovs[aov].buffer[0].r;
-  if (weight) *weight = c->filter_weight_buffer.data();
+  AOVData *a = find_aov(r, aov);
+  if (!a || a->buffer.empty()) return LB_ERR_INVALID;
+  if (buffer) *buffer = &a->buffer[0].r;
+  if (weight) *weight = r->cam->filter_weight_buffer.data();
   return LB_OK;
+}
+
+// AOVData::crypto_hash_map / crypto_total_weight dumped like orc_filter_crypto
+int ref_filter_crypto(ref_camera *r, int aov, int slots, float *ids_out, float *weights_out, float *total_out) {
+  AOVData *a = find_aov(r, aov);
+  if (!a || a->crypto_hash_map.empty()) return -1;
+  size_t mx = 0;
+  for (size_t p = 0; p < a->crypto_hash_map.size(); ++p) {
+    mx = std::max(mx, a->crypto_hash_map[p].size());
+    if (total_out) total_out[p] = a->crypto_total_weight[p];
+    int k = 0;
+    for (auto const &kv : a->crypto_hash_map[p]) {
+      if (k >= slots) break;
+      if (ids_out) ids_out[p * slots + k] = kv.first;
+      if (weights_out) weights_out[p * slots + k] = kv.second;
+      ++k;
+    }
+    for (; k < slots; ++k) {
+      if (ids_out) { const uint32_t nanbits = 0xFFFFFFFFu; memcpy(&ids_out[p * slots + k], &nanbits, 4); }
+      if (weights_out) weights_out[p * slots + k] = 0.0f;
+    }
+  }
+  return (int)mx;
 }
 
 // ---- primitives, straight from the reference headers -------------------------------------------------------

@@ -292,22 +292,47 @@ struct AtAOVSampleIterator {
   float inv_density = 0.f;
   const float *rgba = nullptr;  // [n][4]
   std::map<std::string, ShimAovArray> aovs;
+  // depth sub-samples (AiAOVSampleIteratorGetNextDepth): per sample `depth_n` slots, of which depth_count[i] are valid
+  int depth_n = 0, depth_cur = -1;
+  const uint8_t *depth_count = nullptr;
+  const float *depth_opacity = nullptr;              // [n][depth_n] grey opacity, returned as an RGB of three equal values
+  std::map<std::string, const float *> depth_ids;    // AOV name -> [n][depth_n]
+  float depth_tmp[4] = {0, 0, 0, 0};
 };
 inline AtString AiAOVSampleIteratorGetAOVName(const AtAOVSampleIterator *it) { return it->aov_name; }
 inline void AiAOVSampleIteratorGetPixel(const AtAOVSampleIterator *it, int &x, int &y) { x = it->px; y = it->py; }
-inline void AiAOVSampleIteratorReset(AtAOVSampleIterator *it) { it->cur = -1; }
+inline void AiAOVSampleIteratorReset(AtAOVSampleIterator *it) { it->cur = -1; it->depth_cur = -1; }
 inline bool AiAOVSampleIteratorGetNext(AtAOVSampleIterator *it) {
   long next = it->cur < 0 ? (long)it->begin : it->cur + 1;
   if ((size_t)next >= it->end) { it->cur = (long)it->end; return false; }
   it->cur = next;
   return true;
 }
-inline bool AiAOVSampleIteratorGetNextDepth(AtAOVSampleIterator *) { return false; }
+// walks the depth sub-samples of the current sample; false once they are exhausted (the real iterator then sits on
+// the next sample, which is why the reference re-seeks afterwards, lentil.h:806-808 -- here it stays put)
+inline bool AiAOVSampleIteratorGetNextDepth(AtAOVSampleIterator *it) {
+  if (it->depth_n <= 0 || it->cur < 0) return false;
+  const int count = it->depth_count ? std::min<int>(it->depth_count[it->cur], it->depth_n) : it->depth_n;
+  if (it->depth_cur + 1 < count) { ++it->depth_cur; return true; }
+  it->depth_cur = -1;
+  return false;
+}
 inline AtVector2 AiAOVSampleIteratorGetOffset(const AtAOVSampleIterator *) { return AtVector2(0.f, 0.f); }
 inline float AiAOVSampleIteratorGetInvDensity(const AtAOVSampleIterator *it) { return it->inv_density; }
 inline AtRGBA AiAOVSampleIteratorGetRGBA(const AtAOVSampleIterator *it) { const float *p = it->rgba + 4 * it->cur; return AtRGBA(p[0], p[1], p[2], p[3]); }
 inline const float *shim_aov(const AtAOVSampleIterator *it, const AtString &n) {
   static const float zero[4] = {0, 0, 0, 0};
+  if (it->depth_cur >= 0) {  // inside a depth walk: per-sub-sample values
+    float *tmp = const_cast<float *>(it->depth_tmp);
+    const size_t at = (size_t)it->depth_n * it->cur + it->depth_cur;
+    if (std::string(n.c_str()) == "opacity") {
+      const float o = it->depth_opacity ? it->depth_opacity[at] : 0.0f;
+      tmp[0] = tmp[1] = tmp[2] = tmp[3] = o;
+      return tmp;
+    }
+    auto d = it->depth_ids.find(n.c_str());
+    if (d != it->depth_ids.end() && d->second) { tmp[0] = tmp[1] = tmp[2] = tmp[3] = d->second[at]; return tmp; }
+  }
   auto f = it->aovs.find(n.c_str());
   return (f == it->aovs.end() || !f->second.data) ? zero : f->second.data + 4 * it->cur;
 }

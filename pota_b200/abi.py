@@ -7,7 +7,8 @@ LB_OK = 0
 LB_ERR_INVALID, LB_ERR_NO_DEVICE, LB_ERR_CUDA, LB_ERR_LENS, LB_ERR_STATE, LB_ERR_IMAGE, LB_ERR_COMM = -1, -2, -3, -4, -5, -6, -7
 LB_UNITS_MM, LB_UNITS_CM, LB_UNITS_DM, LB_UNITS_M = 0, 1, 2, 3
 LB_CAMERA_THINLENS, LB_CAMERA_POLYNOMIAL_OPTICS = 0, 1
-LB_FILTER_GAUSSIAN, LB_FILTER_CLOSEST = 0, 1
+LB_FILTER_GAUSSIAN, LB_FILTER_CLOSEST, LB_FILTER_CRYPTO = 0, 1, 2
+LB_CRYPTO_MAX_DEPTH, LB_CRYPTO_DEFAULT_SLOTS, LB_CRYPTO_MAX_SLOTS = 8, 16, 64
 LB_AOV_PLAIN, LB_AOV_RGBA, LB_AOV_LENTIL_DEBUG = 0, 1, 2
 LB_SAMPLE_VOLUME, LB_SAMPLE_IGNORE = 1, 2
 
@@ -124,7 +125,7 @@ class AovDesc(C.Structure):
 
 
 class FrameDesc(C.Structure):
-    _fields_ = [(n, _i) for n in ("xres", "yres", "xres_without_region", "yres_without_region", "region_min_x", "region_min_y")]
+    _fields_ = [(n, _i) for n in ("xres", "yres", "xres_without_region", "yres_without_region", "region_min_x", "region_min_y", "crypto_slots")]
 
 
 class Samples(C.Structure):
@@ -139,8 +140,51 @@ class Samples(C.Structure):
         ("flags", C.c_void_p),
         ("aov_values", C.POINTER(C.c_void_p)),
         ("inv_density", _f),
+        ("crypto_depth", _i),
+        ("crypto_count", C.c_void_p),
+        ("crypto_opacity", C.c_void_p),
+        ("crypto_ids", C.POINTER(C.c_void_p)),
     ]
 
 
 class FilterStats(C.Structure):
-    _fields_ = [(n, C.c_uint64) for n in ("samples", "redistributed", "splats", "attempts", "passthrough")]
+    _fields_ = [(n, C.c_uint64) for n in ("samples", "redistributed", "splats", "attempts", "passthrough", "crypto_dropped")]
+
+
+def host_samples(n_aov, px, py, rgba, pos_cs, inv_density, aov_values=None, raydir=None, transmission=None, flags=None, crypto=None):
+    """lb_samples over HOST numpy arrays -> (Samples, keepalive list).
+
+    crypto: dict(depth=D, opacity=[n][D] float32, ids={aov index: [n][D] float32}, count=[n] uint8 or None).
+    """
+    import numpy as np
+
+    keep = []
+
+    def ptr(a, dt):
+        if a is None:
+            return None
+        a = np.ascontiguousarray(a, dt)
+        keep.append(a)
+        return C.c_void_p(a.ctypes.data)
+
+    n = int(np.asarray(px).shape[0])
+    av = (C.c_void_p * max(n_aov, 1))()
+    for i in range(n_aov):
+        a = None if aov_values is None else aov_values[i]
+        if a is not None:
+            av[i] = ptr(a, np.float32)
+    S = Samples(n, ptr(px, np.int32), ptr(py, np.int32), ptr(rgba, np.float32), ptr(pos_cs, np.float32), ptr(raydir, np.float32),
+                ptr(transmission, np.float32), ptr(flags, np.uint32), av, inv_density)
+    keep.append(av)
+    if crypto is not None:
+        D = int(crypto["depth"])
+        ci = (C.c_void_p * max(n_aov, 1))()
+        for i, a in crypto.get("ids", {}).items():
+            assert np.asarray(a).shape == (n, D)
+            ci[int(i)] = ptr(a, np.float32)
+        S.crypto_depth = D
+        S.crypto_count = ptr(crypto.get("count"), np.uint8)
+        S.crypto_opacity = ptr(crypto.get("opacity"), np.float32)
+        S.crypto_ids = ci
+        keep.append(ci)
+    return S, keep

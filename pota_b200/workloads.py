@@ -110,6 +110,37 @@ def highlight_frame(width: int, height: int, spp: int, tan_fov: float, device="c
     return out
 
 
+def crypto_layers(frame: dict, depth: int, aov_indices, n_ids: int = 10, cell: int = 16, seed: int = 0):
+    """Synthetic cryptomatte depth sub-samples for the samples of `frame` (highlight_frame): what
+    cryptomatte_construct_cache (lentil.h:779-811) reads per sample.  Ids come from a palette of n_ids hash
+    floats (one of them 0.0, some negative) chosen per cell x cell pixel block and layer, so neighbouring
+    pixels share ids like objects do; opacities are multiples of 1/16 (AiColorToGrey of an equal-channel
+    colour is then exact); about one sample in eight has no depth sub-sample at all.
+
+    Returns dict(depth, count uint8 [n], opacity float32 [n, depth], ids {aov index: float32 [n, depth]}).
+    """
+    px, py = frame["px"].to(torch.int64), frame["py"].to(torch.int64)
+    n, dev = px.shape[0], px.device
+    pal_bits = tea8(torch.arange(n_ids, dtype=torch.int64, device=dev), torch.full((n_ids,), 77 + seed, dtype=torch.int64, device=dev))
+    # keep the exponent in a sane range like Cryptomatte's hash_to_float does (no NaN / Inf / denormals)
+    pal_bits = (pal_bits & 0x807FFFFF) | (((pal_bits >> 23) & 0x3F) + 96 << 23)
+    palette = pal_bits.to(torch.int32).view(torch.float32).clone()
+    palette[0] = 0.0
+    k = torch.arange(n, dtype=torch.int64, device=dev)
+    h = tea8(k, torch.full_like(k, 0x2000 + seed))
+    count = (h % (depth + 1)).to(torch.uint8)
+    count[(h >> 8) % 8 == 0] = 0
+    d = torch.arange(depth, dtype=torch.int64, device=dev)[None, :]
+    hd = tea8(k[:, None] * depth + d, torch.full((n, depth), 0x3000 + seed, dtype=torch.int64, device=dev))
+    opacity = ((hd % 17).to(torch.float32) / 16.0).contiguous()
+    cellid = (px // cell) + (py // cell) * 37
+    ids = {}
+    for j, a in enumerate(aov_indices):
+        which = (cellid[:, None] * 3 + d * 5 + j * 7 + ((hd >> 6) % 2)) % n_ids
+        ids[a] = palette[which].contiguous()
+    return dict(depth=depth, count=count.contiguous(), opacity=opacity, ids=ids)
+
+
 def disc_bokeh_image(size: int = 64):
     """A small procedural bokeh kernel (ring + hot centre), float32 [size, size, 3] in [0,1]."""
     import numpy as np

@@ -298,3 +298,45 @@ def test_thinlens_filter_pixel_and_imager(kw):
         np.testing.assert_array_equal(bo, br, err_msg=f"buffer of {aovs[a][0]}")
         np.testing.assert_array_equal(wo, wr)
         np.testing.assert_array_equal(o.resolve(a), r.resolve(a))
+
+
+CRYPTO_AOVS = [("RGBA", 0, 1), ("crypto_material00", 2, 0), ("crypto_material01", 2, 0), ("crypto_object02", 2, 0), ("crypto_asset00", 2, 0)]
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(abb_chromatic=0.4), dict(camera_type=abi.LB_CAMERA_THINLENS, focal_length_lentil=50.0)])
+def test_cryptomatte_accumulate_and_ranked_resolve(kw):
+    """cryptomatte_construct_cache + add_to_buffer_cryptomatte (lentil.h:779-819) and the ranked resolve
+    (lentil_imager.cpp:122-161, including its early row `break`): reference vs oracle, identical tables."""
+    p = po_params(fstop=1.4, focus_dist=35.0, bidir_sample_mult=6, **kw)
+    o, r = orc.OracleCamera(p), ref.RefCamera(p)
+    W, H, spp = 96, 54, 9
+    fr = workloads.highlight_frame(W, H, spp, o.state.tan_fov, "cpu")
+    cr = workloads.crypto_layers(fr, 4, [1, 2, 3, 4])
+    crypto = dict(depth=4, count=cr["count"].numpy(), opacity=cr["opacity"].numpy(), ids={a: v.numpy() for a, v in cr["ids"].items()})
+    args = (fr["px"].numpy(), fr["py"].numpy(), fr["rgba"].numpy(), fr["pos_cs"].numpy(), 1.0 / spp)
+    o.filter_begin(W, H, CRYPTO_AOVS)
+    o.filter_accumulate(*args, crypto=crypto)
+    r.filter_begin(W, H, CRYPTO_AOVS, spp=spp)
+    r.filter_accumulate(*args, crypto=crypto)
+    assert o.filter_stats()["redistributed"] > 50
+    np.testing.assert_array_equal(o.buffers(0)[0], r.buffers(0)[0])
+    sizes = []
+    for a in range(1, len(CRYPTO_AOVS)):
+        io, wo, to, mo = o.crypto(a, 32)
+        ir, wr, tr, mr = r.crypto(a, 32)
+        assert mo == mr and mo <= 32
+        sizes.append(mo)
+        np.testing.assert_array_equal(io.view(np.uint32), ir.view(np.uint32), err_msg=f"ids of {CRYPTO_AOVS[a][0]}")
+        np.testing.assert_array_equal(wo, wr)
+        np.testing.assert_array_equal(to, tr)
+        # whole frame and a bucket; -7 marks what the imager left untouched
+        for box in (dict(), dict(x0=16, y0=8, w=40, h=24)):
+            ro, rr = o.resolve(a, fill=-7.0, **box), r.resolve(a, fill=-7.0, **box)
+            np.testing.assert_array_equal(ro.view(np.uint32), rr.view(np.uint32), err_msg=f"resolve of {CRYPTO_AOVS[a][0]}")
+    assert max(sizes) >= 5  # the scene does reach rank 4
+    # rank-0 coverage of a resolved pixel: ids' weights over the total weight
+    res = o.resolve(1, fill=-7.0)
+    assert np.all(res[..., 1] <= 1.0 + 1e-5) and np.all(res[..., 1] >= res[..., 3]) and np.all(res[..., 1] > 0)
+    res4 = o.resolve(3, fill=-7.0)  # rank 4: most rows end early
+    done = res4[..., 1] != -7.0
+    assert done.any() and (~done).any()
