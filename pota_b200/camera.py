@@ -28,7 +28,7 @@ EXPORTS = [
     "lb_camera_create", "lb_camera_update", "lb_camera_destroy", "lb_camera_get_state", "lb_camera_set_state",
     "lb_camera_create_rays", "lb_camera_create_rays_host", "lb_camera_reverse_rays", "lb_camera_lens_work",
     "lb_filter_begin", "lb_filter_accumulate", "lb_filter_accumulate_host", "lb_filter_get_stats",
-    "lb_filter_newton_iterations", "lb_imager_resolve", "lb_imager_resolve_host", "lb_filter_buffers", "lb_filter_buffers_host",
+    "lb_filter_newton_iterations", "lb_imager_resolve", "lb_imager_resolve_host", "lb_filter_buffers", "lb_filter_buffers_host", "lb_filter_crypto_host",
     "lb_bench_fp32_peak", "lb_bench_red_peak", "lb_camera_set_pupil_geometry", "lb_camera_kernel_kind", "lb_comm_unique_id", "lb_comm_init", "lb_filter_set_sample_base", "lb_filter_reduce", "lb_comm_destroy",
 ]  # fmt: skip
 
@@ -69,6 +69,7 @@ def lib():
         L.lb_imager_resolve_host.argtypes = [vp, i, i, i, i, i, vp]
         L.lb_filter_buffers.argtypes = [vp, i, C.POINTER(vp), C.POINTER(vp)]
         L.lb_filter_buffers_host.argtypes = [vp, i, vp, vp]
+        L.lb_filter_crypto_host.argtypes = [vp, i, vp, vp, C.POINTER(C.c_int)]
         L.lb_bench_fp32_peak.argtypes = [i, C.POINTER(C.c_double)]
         L.lb_camera_kernel_kind.argtypes = [vp]
         L.lb_bench_red_peak.argtypes = [i, i, C.POINTER(C.c_double)]
@@ -197,9 +198,9 @@ class Camera:
         return Ps
 
     # -- lentil_filter / imager_lentil ----------------------------------------------------------
-    def filter_begin(self, xres: int, yres: int, aovs, xres_full=None, yres_full=None, region_min=(0, 0)):
+    def filter_begin(self, xres: int, yres: int, aovs, xres_full=None, yres_full=None, region_min=(0, 0), crypto_slots: int = 0):
         """aovs: list of (name, LB_FILTER_*, LB_AOV_*).  setup_filter: allocates zeroed device framebuffers."""
-        self._frame = abi.FrameDesc(xres, yres, xres_full or xres, yres_full or yres, region_min[0], region_min[1])
+        self._frame = abi.FrameDesc(xres, yres, xres_full or xres, yres_full or yres, region_min[0], region_min[1], crypto_slots)
         arr = (abi.AovDesc * len(aovs))()
         for k, (name, flt, role) in enumerate(aovs):
             arr[k].name = name.encode()
@@ -208,21 +209,34 @@ class Camera:
         self._aovs = list(aovs)
         _check(lib().lb_filter_begin(self._h, C.byref(self._frame), len(aovs), arr))
 
-    def _samples(self, px, py, rgba, pos_cs, inv_density, aov_values, raydir, transmission, flags, ptr):
+    def _samples(self, px, py, rgba, pos_cs, inv_density, aov_values, raydir, transmission, flags, ptr, crypto=None):
         n = int(px.shape[0])
         av = (C.c_void_p * max(len(self._aovs), 1))()
         for k in range(len(self._aovs)):
             a = None if aov_values is None else aov_values[k]
             av[k] = None if a is None else ptr(a).value
-        return abi.Samples(n, ptr(px), ptr(py), ptr(rgba), ptr(pos_cs), ptr(raydir), ptr(transmission), ptr(flags), av, inv_density), av
+        S = abi.Samples(n, ptr(px), ptr(py), ptr(rgba), ptr(pos_cs), ptr(raydir), ptr(transmission), ptr(flags), av, inv_density)
+        keep = [av]
+        if crypto is not None:  # dict(depth, opacity [n, depth], ids {aov index: [n, depth]}, count [n] uint8 or None)
+            ci = (C.c_void_p * max(len(self._aovs), 1))()
+            for k, a in crypto.get("ids", {}).items():
+                assert tuple(a.shape) == (n, int(crypto["depth"])), "crypto ids must be [n, depth]"
+                ci[int(k)] = ptr(a).value
+            S.crypto_depth = int(crypto["depth"])
+            S.crypto_count = ptr(crypto.get("count"))
+            S.crypto_opacity = ptr(crypto.get("opacity"))
+            S.crypto_ids = ci
+            keep.append(ci)
+        return S, keep
 
-    def filter_accumulate(self, px, py, rgba, pos_cs, inv_density, aov_values=None, raydir=None, transmission=None, flags=None, stream=None):
+    def filter_accumulate(self, px, py, rgba, pos_cs, inv_density, aov_values=None, raydir=None, transmission=None, flags=None, stream=None,
+                          crypto=None):
         """filter_pixel (RGBA branch) for a device-resident batch of samples."""
-        S, keep = self._samples(px, py, rgba, pos_cs, inv_density, aov_values, raydir, transmission, flags, _dptr)
+        S, keep = self._samples(px, py, rgba, pos_cs, inv_density, aov_values, raydir, transmission, flags, _dptr, crypto)
         _check(lib().lb_filter_accumulate(self._h, C.byref(S), _stream_ptr(stream)))
 
-    def filter_accumulate_host(self, px, py, rgba, pos_cs, inv_density, aov_values=None, raydir=None, transmission=None, flags=None):
-        S, keep = self._samples(px, py, rgba, pos_cs, inv_density, aov_values, raydir, transmission, flags, _hptr)
+    def filter_accumulate_host(self, px, py, rgba, pos_cs, inv_density, aov_values=None, raydir=None, transmission=None, flags=None, crypto=None):
+        S, keep = self._samples(px, py, rgba, pos_cs, inv_density, aov_values, raydir, transmission, flags, _hptr, crypto)
         _check(lib().lb_filter_accumulate_host(self._h, C.byref(S)))
 
     def filter_stats(self) -> dict:
@@ -234,8 +248,9 @@ class Camera:
         d["newton_its"] = its.value
         return d
 
-    def resolve(self, aov: int, x0=None, y0=None, w=None, h=None, stream=None):
-        """driver_process_bucket for one bucket (default: the whole region) -> device tensor [h, w, 4]."""
+    def resolve(self, aov: int, x0=None, y0=None, w=None, h=None, stream=None, fill: float = 0.0):
+        """driver_process_bucket for one bucket (default: the whole region) -> device tensor [h, w, 4].
+        fill: what the bucket holds beforehand; cryptomatte rows can end early and keep it (lentil_imager.cpp:132-134)."""
         import torch
 
         f = self._frame
@@ -243,14 +258,14 @@ class Camera:
         y0 = f.region_min_y if y0 is None else y0
         w = f.xres if w is None else w
         h = f.yres if h is None else h
-        out = torch.empty((h, w, 4), dtype=torch.float32, device=f"cuda:{self.device}")
+        out = torch.full((h, w, 4), fill, dtype=torch.float32, device=f"cuda:{self.device}")
         _check(lib().lb_imager_resolve(self._h, aov, x0, y0, w, h, _dptr(out), _stream_ptr(stream)))
         return out
 
     def resolve_host(self, aov: int, out: np.ndarray | None = None):
         f = self._frame
         if out is None:
-            out = np.empty((f.yres, f.xres, 4), np.float32)
+            out = np.zeros((f.yres, f.xres, 4), np.float32)
         _check(lib().lb_imager_resolve_host(self._h, aov, f.region_min_x, f.region_min_y, f.xres, f.yres, _hptr(out)))
         return out
 
@@ -261,6 +276,17 @@ class Camera:
         wgt = np.empty((f.yres, f.xres), np.float32)
         _check(lib().lb_filter_buffers_host(self._h, aov, _hptr(buf), _hptr(wgt)))
         return buf, wgt
+
+    def crypto(self, aov: int):
+        """AOVData::crypto_hash_map of a cryptomatte AOV as numpy tables: (ids [yres, xres, slots] float32 with NaN
+        (all bits set) in unused slots, weights [yres, xres, slots], crypto_total_weight [yres, xres])."""
+        f = self._frame
+        slots = C.c_int()
+        _check(lib().lb_filter_crypto_host(self._h, aov, None, None, C.byref(slots)))
+        ids = np.empty((f.yres, f.xres, slots.value), np.float32)
+        wts = np.empty((f.yres, f.xres, slots.value), np.float32)
+        _check(lib().lb_filter_crypto_host(self._h, aov, _hptr(ids), _hptr(wts), None))
+        return ids, wts, self.buffers(aov)[0][..., 0].copy()
 
     def buffer_pointers(self, aov: int):
         """Device addresses of the raw accumulators (owned by the camera)."""

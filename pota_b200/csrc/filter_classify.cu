@@ -30,6 +30,35 @@ __device__ float additional_luminance_soft_trans(const FilterConsts &fc, float l
   return 0.0f;
 }
 
+// cryptomatte_construct_cache (lentil.h:779-811) for AOV `a` of sample i: walks the depth sub-samples in order,
+// merging equal ids as the reference's std::map<float,float> does, and leaves the packed {id, weight} list in the
+// batch scratch for the splat kernel.  Float arithmetic operation by operation as there (this unit is -fmad=false).
+__device__ void crypto_build_cache(const AovSet &aovs, const SampleIO &s, int a, size_t i) {
+  const int D = aovs.crypto_depth;
+  const int stride = D > 1 ? D : 1;
+  float key[kCryptoMaxDepth], wgt[kCryptoMaxDepth];
+  int m = 0;
+  auto add = [&](float k, float v) {
+    for (int j = 0; j < m; ++j)
+      if (key[j] == k) { wgt[j] += v; return; }
+    key[m] = k; wgt[m] = 0.0f + v; ++m;
+  };
+  float iterative_transparency_weight = 1.0f, quota = 1.0f, sample_value = 0.0f;
+  const float *ids = aovs.crypto_ids[a];
+  int count = !ids ? 0 : (s.crypto_count ? min((int)__ldg(s.crypto_count + i), D) : D);
+  for (int d = 0; d < count; ++d) {
+    const float sub_sample_opacity = s.crypto_opacity ? __ldg(s.crypto_opacity + i * (size_t)D + d) : 0.0f;
+    sample_value = __ldg(ids + i * (size_t)D + d);
+    const float sub_sample_weight = sub_sample_opacity * iterative_transparency_weight;
+    iterative_transparency_weight *= (1.0f - sub_sample_opacity);
+    quota -= sub_sample_weight;
+    add(sample_value, sub_sample_weight);
+  }
+  if ((double)quota > 0.0) add(sample_value, quota);
+  float2 *out = aovs.crypto_cache[a] + i * (size_t)stride;
+  for (int j = 0; j < stride; ++j) out[j] = j < m ? make_float2(key[j], wgt[j]) : make_float2(__uint_as_float(kCryptoFree), 0.0f);
+}
+
 __global__ void __launch_bounds__(256)
 k_filter_classify(const __grid_constant__ FilterConsts fc, const __grid_constant__ AovSet aovs, const __grid_constant__ SampleIO s,
                   WorkItem *__restrict__ work, FilterCounters *__restrict__ counters, uint64_t sample_base) {
@@ -77,11 +106,14 @@ k_filter_classify(const __grid_constant__ FilterConsts fc, const __grid_constant
     const float debug_val = (float)(samples * (redistribute ? 1 : 0));  // lentil_debug value, taken at :209-211
     if (fc.camera_type == 1 && (double)fabsf(csp[2]) < fc.lens_length_tenth) redistribute = false;  // :240, PolynomialOptics case only
     const int px = __ldg(s.px + i), py = __ldg(s.py + i);
+    for (int a = 0; a < fc.n_aov; ++a)  // lentil_filter.cpp:167-169
+      if (aovs.filter[a] == 2) crypto_build_cache(aovs, s, a, i);
     if (!redistribute) {
       // filter_and_add_to_buffer_new (lentil.h:938-955): every AOV, own pixel, weight inv_density
       const unsigned pixel = (unsigned)fc.xres * (unsigned)py + (unsigned)px;
       const float white[3] = {1.f, 1.f, 1.f};
       for (int a = 0; a < fc.n_aov; ++a) {
+        if (aovs.filter[a] == 2) { crypto_add(aovs, a, i, true, pixel, s.inv_density, counters); continue; }
         const float4 v = aov_value(aovs, s, a, i, debug_val);
         add_to_buffer(aovs, a, pixel, v, 0.0f, depth, s.inv_density, white, sample_base + i);
       }

@@ -7,6 +7,7 @@ namespace lb {
 
 // value of AOV `a` for sample i as filter_pixel gathers it (lentil_filter.cpp:206-234)
 LB_DEV float4 aov_value(const AovSet &aovs, const SampleIO &s, int a, size_t i, float debug_val) {
+  if (aovs.filter[a] == 2 /*LB_FILTER_CRYPTO: no value, lentil_filter.cpp:208*/) return make_float4(0.f, 0.f, 0.f, 0.f);
   if (aovs.role[a] == 2 /*LB_AOV_LENTIL_DEBUG*/) return make_float4(debug_val, debug_val, debug_val, debug_val);
   const float4 *src = aovs.values[a] ? aovs.values[a] : s.rgba;
   return __ldg(src + i);
@@ -37,6 +38,55 @@ LB_DEV void add_to_buffer(const AovSet &aovs, int a, unsigned pixel, float4 v, f
   } else {
     if (aovs.role[a] != 2) atomicMin(aovs.zkey + pixel, closest_key(depth, sample_global));
     else if (v.x != 0.0f) atomicMin(aovs.zkey_debug + pixel, closest_key(depth, sample_global));
+  }
+}
+
+// ---- cryptomatte ----------------------------------------------------------------------------------
+// aov.crypto_hash_map[px][id] += w (lentil.h:817) on a fixed-size open-addressed table: claim a slot with a
+// compare-and-swap on the id bits, then a float reduction on its weight.
+LB_DEV void crypto_insert(uint32_t *__restrict__ keys, float *__restrict__ wgts, int slots, unsigned pixel, float id, float w,
+                          FilterCounters *counters) {
+  const uint32_t key = __float_as_uint(id == 0.0f ? 0.0f : id);  // -0 and +0 are one std::map key
+  uint32_t *k0 = keys + (size_t)pixel * slots;
+  float *w0 = wgts + (size_t)pixel * slots;
+  unsigned h = ((key * 2654435761u) >> 15) % (unsigned)slots;
+  for (int t = 0; t < slots; ++t) {
+    uint32_t cur = *(volatile uint32_t *)(k0 + h);
+    if (cur == kCryptoFree) cur = atomicCAS(k0 + h, kCryptoFree, key);
+    if (cur == kCryptoFree || cur == key) {
+      atomicAdd(w0 + h, w);
+      return;
+    }
+    h = h + 1 == (unsigned)slots ? 0u : h + 1;
+  }
+  atomicAdd(&counters->crypto_dropped, 1ull);
+}
+
+// add_to_buffer_cryptomatte (lentil.h:814-819) for AOV `a` and the cached {id, weight} list of source sample i.
+// Called warp-converged from the splat kernels (`on`: this lane has a splat at `pixel`), per thread from classify.
+LB_DEV void crypto_add(const AovSet &aovs, int a, size_t i, bool on, unsigned pixel, float sample_weight, FilterCounters *counters) {
+  const int stride = aovs.crypto_depth > 1 ? aovs.crypto_depth : 1;
+  const float2 *e = aovs.crypto_cache[a] + i * (size_t)stride;
+  if (on) atomicAdd(&aovs.buffer[a][pixel].x, sample_weight);  // crypto_total_weight
+  for (int j = 0; j < stride; ++j) {
+    const float2 kv = e[j];
+    if (__float_as_uint(kv.x) == kCryptoFree) break;
+    if (on) crypto_insert(aovs.crypto_key[a], aovs.crypto_wgt[a], aovs.crypto_slots, pixel, kv.x, kv.y * sample_weight, counters);
+  }
+}
+
+// every AOV of one splat (lentil_filter.cpp:295-298 / :442-445).  Warp-converged: the source sample i and with it
+// the AOV values are warp-uniform, the target pixel is per lane (< 0: this lane has nothing to add).
+LB_DEV void splat_all_aovs(const FilterConsts &fc, const AovSet &aovs, const SampleIO &s, size_t i, float debug_val, int pixel,
+                           float add_energy, float depth, float weight, const float rgb_weight[3], uint64_t sample_global,
+                           FilterCounters *counters) {
+  for (int a = 0; a < fc.n_aov; ++a) {
+    if (aovs.filter[a] == 2) {
+      crypto_add(aovs, a, i, pixel >= 0, (unsigned)pixel, weight, counters);
+    } else {
+      const float4 v = aov_value(aovs, s, a, i, debug_val);
+      if (pixel >= 0) add_to_buffer(aovs, a, (unsigned)pixel, v, add_energy, depth, weight, rgb_weight, sample_global);
+    }
   }
 }
 

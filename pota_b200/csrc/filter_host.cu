@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cstring>
 #include <mutex>
+#include <string>
 #include <vector>
 
 #include "../../include/lentil_b200.h"
@@ -41,6 +42,14 @@ struct FilterState {
   WorkItem *work = nullptr;
   size_t work_cap = 0;
   uint16_t *debug_samples = nullptr;
+  // cryptomatte: per crypto AOV one table of [npx][crypto_slots] id bits followed by [npx][crypto_slots] weights
+  int n_crypto = 0, crypto_slots = 0;
+  int crypto_of[kMaxAov]{};          // AOV index -> crypto table index, -1 for the others
+  int crypto_rank[kMaxAov]{};        // 0 / 2 / 4 from the AOV name (lentil_imager.cpp:124-126)
+  uint32_t *crypto_tables = nullptr; // n_crypto tables back to back
+  size_t crypto_table_words = 0;     // 2 * npx * crypto_slots
+  float2 *crypto_cache = nullptr;    // batch scratch [n_crypto][work_cap][crypto_cache_stride]
+  int crypto_cache_stride = 0;
   FilterCounters *d_counters = nullptr;
   uint64_t sample_base = 0;
   // host-path staging
@@ -78,6 +87,7 @@ struct NcclApi {
   decltype(&ncclCommDestroy) CommDestroy = nullptr;
   decltype(&ncclAllReduce) AllReduce = nullptr;
   decltype(&ncclReduce) Reduce = nullptr;
+  decltype(&ncclBroadcast) Broadcast = nullptr;
   decltype(&ncclGroupStart) GroupStart = nullptr;
   decltype(&ncclGroupEnd) GroupEnd = nullptr;
   decltype(&ncclGetErrorString) GetErrorString = nullptr;
@@ -94,7 +104,7 @@ NcclApi *load_nccl() {
     }
     if (!api.h) return;
 #define SYM(f) api.f = (decltype(api.f))dlsym(api.h, "nccl" #f)
-    SYM(GetUniqueId); SYM(CommInitRank); SYM(CommDestroy); SYM(AllReduce); SYM(Reduce); SYM(GroupStart); SYM(GroupEnd); SYM(GetErrorString);
+    SYM(GetUniqueId); SYM(CommInitRank); SYM(CommDestroy); SYM(AllReduce); SYM(Reduce); SYM(Broadcast); SYM(GroupStart); SYM(GroupEnd); SYM(GetErrorString);
 #undef SYM
   });
   return (api.h && api.GetUniqueId && api.CommInitRank && api.AllReduce && api.Reduce) ? &api : nullptr;
@@ -129,13 +139,24 @@ void fill_consts(lb_camera *c, const FilterState *f, FilterConsts &fc) {
   fc.aspect_full = (double)f->frame.xres_without_region / (double)f->frame.yres_without_region;
 }
 
-void fill_aovs(const FilterState *f, AovSet &A, const float *const *values) {
+void fill_aovs(const FilterState *f, AovSet &A, const lb_samples *S) {
   memset(&A, 0, sizeof A);
+  const float *const *values = S ? S->aov_values : nullptr;
+  A.crypto_slots = f->crypto_slots;
+  A.crypto_depth = S ? S->crypto_depth : 0;
   for (int a = 0; a < f->n_aov; ++a) {
     A.buffer[a] = (float4 *)(f->block + (size_t)a * f->npx * 4);
     A.values[a] = values ? (const float4 *)values[a] : nullptr;
     A.filter[a] = f->aovs[a].filter;
     A.role[a] = f->aovs[a].role;
+    const int t = f->crypto_of[a];
+    if (t >= 0) {
+      A.values[a] = nullptr;
+      A.crypto_key[a] = f->crypto_tables + (size_t)t * f->crypto_table_words;
+      A.crypto_wgt[a] = (float *)(A.crypto_key[a] + f->crypto_table_words / 2);
+      A.crypto_ids[a] = (S && S->crypto_depth > 0 && S->crypto_ids) ? S->crypto_ids[a] : nullptr;
+      A.crypto_cache[a] = f->crypto_cache ? f->crypto_cache + (size_t)t * f->work_cap * f->crypto_cache_stride : nullptr;
+    }
   }
   A.weight = f->block + (size_t)f->n_aov * f->npx * 4;
   A.zkey = f->zkey;
@@ -143,13 +164,17 @@ void fill_aovs(const FilterState *f, AovSet &A, const float *const *values) {
   A.debug_samples = f->has_debug_closest ? f->debug_samples : nullptr;
 }
 
-int ensure_batch_capacity(FilterState *f, size_t n) {
-  if (f->work_cap >= n) return LB_OK;
-  cudaFree(f->work); cudaFree(f->debug_samples);
-  f->work = nullptr; f->debug_samples = nullptr; f->work_cap = 0;
+int ensure_batch_capacity(FilterState *f, size_t n, int crypto_depth) {
+  const int stride = f->n_crypto ? std::max(crypto_depth, 1) : 0;
+  if (f->work_cap >= n && f->crypto_cache_stride >= stride) return LB_OK;
+  n = std::max(n, f->work_cap);
+  cudaFree(f->work); cudaFree(f->debug_samples); cudaFree(f->crypto_cache);
+  f->work = nullptr; f->debug_samples = nullptr; f->crypto_cache = nullptr; f->work_cap = 0; f->crypto_cache_stride = 0;
   CUF(cudaMalloc(&f->work, n * sizeof(WorkItem)));
   CUF(cudaMalloc(&f->debug_samples, n * sizeof(uint16_t)));
+  if (stride) CUF(cudaMalloc(&f->crypto_cache, (size_t)f->n_crypto * n * stride * sizeof(float2)));
   f->work_cap = n;
+  f->crypto_cache_stride = stride;
   return LB_OK;
 }
 
@@ -157,14 +182,16 @@ int ensure_batch_capacity(FilterState *f, size_t n) {
 int accumulate_device(lb_camera *c, FilterState *f, const lb_samples *S, cudaStream_t stream) {
   if (S->n == 0) return LB_OK;
   if (S->n > 0xFFFFFFFFull) return lb_fail(LB_ERR_INVALID, "batch larger than 2^32 samples");
-  int rc = ensure_batch_capacity(f, S->n);
+  if (S->crypto_depth < 0 || S->crypto_depth > LB_CRYPTO_MAX_DEPTH) return lb_fail(LB_ERR_INVALID, "crypto_depth outside [0, LB_CRYPTO_MAX_DEPTH]");
+  int rc = ensure_batch_capacity(f, S->n, S->crypto_depth);
   if (rc != LB_OK) return rc;
   FilterConsts fc;
   fill_consts(c, f, fc);
   AovSet A;
-  fill_aovs(f, A, S->aov_values);
+  fill_aovs(f, A, S);
   SampleIO io{S->n, S->px, S->py, (const float4 *)S->rgba, (const float4 *)S->pos_cs, (const float4 *)S->raydir,
-              (const float4 *)S->transmission, S->flags, S->inv_density};
+              (const float4 *)S->transmission, S->flags, S->inv_density,
+              f->n_crypto && S->crypto_depth > 0 ? S->crypto_count : nullptr, f->n_crypto && S->crypto_depth > 0 ? S->crypto_opacity : nullptr};
   CUF(cudaMemsetAsync(&f->d_counters->work_count, 0, 2 * sizeof(unsigned), stream));
   CUF(launch_filter_classify(fc, A, io, f->work, f->d_counters, f->sample_base, stream));
   if (cam_params(c).camera_type == LB_CAMERA_THINLENS)
@@ -190,6 +217,7 @@ void filter_state_destroy(FilterState *f) {
   if (!f) return;
   if (f->comm) { if (NcclApi *n = load_nccl()) n->CommDestroy(f->comm); }
   cudaFree(f->block); cudaFree(f->zkey); cudaFree(f->zkey_debug); cudaFree(f->work); cudaFree(f->debug_samples);
+  cudaFree(f->crypto_tables); cudaFree(f->crypto_cache);
   cudaFree(f->d_counters); cudaFree(f->stage);
   if (f->stream) cudaStreamDestroy(f->stream);
   delete f;
@@ -219,6 +247,37 @@ int lb_filter_begin(lb_camera *c, const lb_frame_desc *frame, int n_aov, const l
     f->block_floats = floats;
   }
   f->npx = npx;
+  // cryptomatte tables (AOVData::allocate_cryptomatte_buffers, aov_data.h:145-150)
+  int n_crypto = 0;
+  for (int a = 0; a < n_aov; ++a) {
+    f->crypto_of[a] = -1;
+    f->crypto_rank[a] = 0;
+    if (aovs[a].filter != LB_FILTER_CRYPTO) continue;
+    char name[65] = {0};
+    memcpy(name, aovs[a].name, 64);
+    if (!strstr(name, "crypto_")) return lb_fail(LB_ERR_INVALID, "LB_FILTER_CRYPTO AOV whose name has no \"crypto_\" (lentil.h:1036)");
+    for (const char *k : {"crypto_material", "crypto_asset", "crypto_object"}) {  // lentil_imager.cpp:124-126
+      if (std::string(name) == std::string(k) + "01") f->crypto_rank[a] = 2;
+      if (std::string(name) == std::string(k) + "02") f->crypto_rank[a] = 4;
+    }
+    f->crypto_of[a] = n_crypto++;
+  }
+  const int slots = frame->crypto_slots > 0 ? frame->crypto_slots : LB_CRYPTO_DEFAULT_SLOTS;
+  if (n_crypto && slots > LB_CRYPTO_MAX_SLOTS) return lb_fail(LB_ERR_INVALID, "crypto_slots above LB_CRYPTO_MAX_SLOTS");
+  const size_t table_words = n_crypto ? 2 * npx * (size_t)slots : 0;
+  if (n_crypto != f->n_crypto || table_words != f->crypto_table_words) {
+    cudaFree(f->crypto_tables); cudaFree(f->crypto_cache);
+    f->crypto_tables = nullptr; f->crypto_cache = nullptr; f->crypto_cache_stride = 0;
+    if (n_crypto) CUF(cudaMalloc(&f->crypto_tables, (size_t)n_crypto * table_words * 4));
+    f->n_crypto = n_crypto;
+    f->crypto_table_words = table_words;
+  }
+  f->crypto_slots = n_crypto ? slots : 0;
+  for (int t = 0; t < n_crypto; ++t) {
+    uint32_t *tab = f->crypto_tables + (size_t)t * table_words;
+    CUF(cudaMemset(tab, 0xFF, table_words / 2 * 4));               // ids: kCryptoFree
+    CUF(cudaMemset(tab + table_words / 2, 0, table_words / 2 * 4)); // weights
+  }
   f->has_closest = f->has_debug_closest = false;
   for (int a = 0; a < n_aov; ++a)
     if (aovs[a].filter == LB_FILTER_CLOSEST) (aovs[a].role == LB_AOV_LENTIL_DEBUG ? f->has_debug_closest : f->has_closest) = true;
@@ -260,8 +319,13 @@ int lb_filter_accumulate_host(lb_camera *c, const lb_samples *S) {
   int n_val = 0;
   for (int a = 0; a < f->n_aov; ++a) if (S->aov_values && S->aov_values[a]) ++n_val;
   // per-sample bytes: px,py (8) + rgba,pos (32) + raydir,transmission (32) + flags (4) + values
-  const size_t per = 8 + 32 + (S->raydir ? 16 : 0) + (S->transmission ? 16 : 0) + (S->flags ? 4 : 0) + 16 * (size_t)n_val;
-  const size_t need = per * chunk + 256 * 16;
+  if (S->crypto_depth < 0 || S->crypto_depth > LB_CRYPTO_MAX_DEPTH) return lb_fail(LB_ERR_INVALID, "crypto_depth outside [0, LB_CRYPTO_MAX_DEPTH]");
+  const size_t Dn = f->n_crypto ? (size_t)S->crypto_depth : 0;
+  int n_ids = 0;
+  for (int a = 0; a < f->n_aov; ++a) if (Dn && S->crypto_ids && S->crypto_ids[a]) ++n_ids;
+  const size_t per = 8 + 32 + (S->raydir ? 16 : 0) + (S->transmission ? 16 : 0) + (S->flags ? 4 : 0) + 16 * (size_t)n_val +
+                     (Dn ? 1 + 4 * Dn * (1 + (size_t)n_ids) : 0);
+  const size_t need = per * chunk + 256 * (16 + 2 * kMaxAov);
   if (f->stage_bytes < need) {
     cudaFree(f->stage); f->stage = nullptr; f->stage_bytes = 0;
     CUF(cudaMalloc(&f->stage, need));
@@ -289,6 +353,13 @@ int lb_filter_accumulate_host(lb_camera *c, const lb_samples *S) {
     D.px = (const int32_t *)put(S->px, 4);
     D.py = (const int32_t *)put(S->py, 4);
     D.flags = (const uint32_t *)put(S->flags, 4);
+    const float *cids[kMaxAov] = {nullptr};
+    if (Dn) {
+      D.crypto_opacity = (const float *)put(S->crypto_opacity, 4 * Dn);
+      for (int a = 0; a < f->n_aov; ++a) cids[a] = (S->crypto_ids && S->crypto_ids[a]) ? (const float *)put(S->crypto_ids[a], 4 * Dn) : nullptr;
+      D.crypto_ids = cids;
+      D.crypto_count = (const uint8_t *)put(S->crypto_count, 1);
+    }
     CUF(cudaGetLastError());
     int rc = accumulate_device(c, f, &D, f->stream);
     if (rc != LB_OK) return rc;
@@ -307,6 +378,7 @@ int lb_filter_get_stats(lb_camera *c, lb_filter_stats *out) {
   CUF(cudaMemcpy(&h, f->d_counters, sizeof h, cudaMemcpyDeviceToHost));
   out->samples = h.samples; out->redistributed = h.redistributed; out->splats = h.splats;
   out->attempts = h.attempts; out->passthrough = h.passthrough;
+  out->crypto_dropped = h.crypto_dropped;
   return LB_OK;
 }
 
@@ -329,6 +401,12 @@ int lb_imager_resolve(lb_camera *c, int aov, int x0, int y0, int w, int h, float
   const int rx = x0 - f->frame.region_min_x, ry = y0 - f->frame.region_min_y;
   if (rx < 0 || ry < 0 || w < 0 || h < 0 || rx + w > f->frame.xres || ry + h > f->frame.yres) return lb_fail(LB_ERR_INVALID, "bucket outside the region");
   DeviceGuard g(cam_device(c));
+  if (f->crypto_of[aov] >= 0) {
+    const uint32_t *key = f->crypto_tables + (size_t)f->crypto_of[aov] * f->crypto_table_words;
+    CUF(launch_resolve_crypto(key, (const float *)(key + f->crypto_table_words / 2), (const float4 *)(f->block + (size_t)aov * f->npx * 4),
+                              f->crypto_slots, f->crypto_rank[aov], f->frame.xres, rx, ry, w, h, (float4 *)rgba_out, (cudaStream_t)stream));
+    return LB_OK;
+  }
   CUF(launch_resolve((const float4 *)(f->block + (size_t)aov * f->npx * 4), f->block + (size_t)f->n_aov * f->npx * 4, f->aovs[aov].filter,
                      f->aovs[aov].role, f->frame.xres, rx, ry, w, h, (float4 *)rgba_out, (cudaStream_t)stream));
   return LB_OK;
@@ -343,6 +421,9 @@ int lb_imager_resolve_host(lb_camera *c, int aov, int x0, int y0, int w, int h, 
   const size_t bytes = (size_t)std::max(w, 0) * std::max(h, 0) * 16;
   if (bytes == 0) return LB_OK;
   CUF(cudaMalloc(&d, bytes));
+  CUF(cudaDeviceSynchronize());  // accumulates may still be running on the caller's streams
+  if (aov >= 0 && aov < f->n_aov && f->crypto_of[aov] >= 0)  // cryptomatte rows can end early and keep the bucket's contents
+    CUF(cudaMemcpyAsync(d, rgba_out, bytes, cudaMemcpyHostToDevice, f->stream));
   int rc = lb_imager_resolve(c, aov, x0, y0, w, h, d, f->stream);
   if (rc == LB_OK) {
     cudaError_t e = cudaMemcpyAsync(rgba_out, d, bytes, cudaMemcpyDeviceToHost, f->stream);
@@ -370,6 +451,20 @@ int lb_filter_buffers_host(lb_camera *c, int aov, float *buffer_out, float *weig
   CUF(cudaDeviceSynchronize());
   if (buffer_out) CUF(cudaMemcpy(buffer_out, f->block + (size_t)aov * f->npx * 4, f->npx * 16, cudaMemcpyDeviceToHost));
   if (weight_out) CUF(cudaMemcpy(weight_out, f->block + (size_t)f->n_aov * f->npx * 4, f->npx * 4, cudaMemcpyDeviceToHost));
+  return LB_OK;
+}
+
+int lb_filter_crypto_host(lb_camera *c, int aov, float *ids_out, float *weights_out, int *slots_out) {
+  FilterState *f = c ? cam_filter(c) : nullptr;
+  if (!f) return lb_fail(LB_ERR_STATE, "lb_filter_begin has not been called");
+  if (aov < 0 || aov >= f->n_aov || f->crypto_of[aov] < 0) return lb_fail(LB_ERR_INVALID, "not a cryptomatte AOV");
+  DeviceGuard g(cam_device(c));
+  CUF(cudaDeviceSynchronize());
+  const uint32_t *key = f->crypto_tables + (size_t)f->crypto_of[aov] * f->crypto_table_words;
+  const size_t half = f->crypto_table_words / 2;
+  if (ids_out) CUF(cudaMemcpy(ids_out, key, half * 4, cudaMemcpyDeviceToHost));
+  if (weights_out) CUF(cudaMemcpy(weights_out, key + half, half * 4, cudaMemcpyDeviceToHost));
+  if (slots_out) *slots_out = f->crypto_slots;
   return LB_OK;
 }
 
@@ -424,6 +519,29 @@ int lb_filter_reduce(lb_camera *c, int root, lb_stream stream_) {
     }
     CUF(cudaMemcpyAsync(local, global, f->npx * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, stream));
     CUF(cudaFreeAsync(global, stream));
+  }
+  // cryptomatte tables: every rank's tables are broadcast in turn and folded into the receivers' own
+  // (ids differ per rank, so this is a merge, not an element-wise reduction).  crypto_total_weight rides in the
+  // AOV plane and is summed below.
+  if (f->n_crypto) {
+    if (!n->Broadcast) return lb_fail(LB_ERR_COMM, "ncclBroadcast unavailable");
+    const size_t words = (size_t)f->n_crypto * f->crypto_table_words;
+    uint32_t *mine = nullptr, *other = nullptr;
+    CUF(cudaMallocAsync(&mine, words * 4, stream));   // snapshot: what this rank contributes
+    CUF(cudaMallocAsync(&other, words * 4, stream));
+    CUF(cudaMemcpyAsync(mine, f->crypto_tables, words * 4, cudaMemcpyDeviceToDevice, stream));
+    for (int r = 0; r < f->world; ++r) {
+      if ((rc = check(n->Broadcast(mine, other, words, ncclUint32, r, f->comm, stream))) != LB_OK) return rc;
+      if (r == f->rank || (root >= 0 && f->rank != root)) continue;
+      for (int t = 0; t < f->n_crypto; ++t) {
+        uint32_t *key = f->crypto_tables + (size_t)t * f->crypto_table_words;
+        const uint32_t *okey = other + (size_t)t * f->crypto_table_words;
+        const size_t half = f->crypto_table_words / 2;
+        CUF(launch_crypto_merge(key, (float *)(key + half), okey, (const float *)(okey + half), f->npx, f->crypto_slots, f->d_counters, stream));
+      }
+    }
+    CUF(cudaFreeAsync(mine, stream));
+    CUF(cudaFreeAsync(other, stream));
   }
   // one sum-reduce over every AOV plane + the weight plane
   if (root < 0) rc = check(n->AllReduce(f->block, f->block, f->block_floats, ncclFloat32, ncclSum, f->comm, stream));

@@ -57,6 +57,72 @@ __global__ void k_resolve(const float4 *__restrict__ buffer, const float *__rest
   out[(size_t)j * w + i] = v;
 }
 
+// Ranked cryptomatte resolve, lentil_imager.cpp:122-161.  One block per bucket row because of the reference's
+// `break` (:132-134): the first pixel of the row with <= rank ids ends the row, it and everything after it keep
+// what the caller's bucket held.  Order: weight descending (compareTail, :11-16); equal weights stay in ascending-id
+// order, which is what std::sort's insertion sort leaves for the map-ordered input of up to 16 entries.
+__global__ void __launch_bounds__(256)
+k_resolve_crypto(const uint32_t *__restrict__ key, const float *__restrict__ wgt, const float4 *__restrict__ total, int slots, int rank,
+                 int xres, int x0, int y0, int w, float4 *__restrict__ out) {
+  __shared__ int first_break;
+  const int j = blockIdx.x;
+  if (threadIdx.x == 0) first_break = w;
+  __syncthreads();
+  for (int i = threadIdx.x; i < w; i += blockDim.x) {
+    const size_t p = (size_t)(y0 + j) * xres + (x0 + i);
+    int size = 0;
+    for (int k = 0; k < slots; ++k) size += key[p * slots + k] != kCryptoFree;
+    if (size <= rank) atomicMin(&first_break, i);
+  }
+  __syncthreads();
+  const int end = first_break;
+  for (int i = threadIdx.x; i < end; i += blockDim.x) {
+    const size_t p = (size_t)(y0 + j) * xres + (x0 + i);
+    const uint32_t *kp = key + p * slots;
+    const float *wp = wgt + p * slots;
+    const float tw = total[p].x;  // crypto_total_weight
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int e = 0; e < slots; ++e) {
+      if (kp[e] == kCryptoFree) continue;
+      const float ide = __uint_as_float(kp[e]), we = wp[e];
+      int before = 0;
+      for (int f = 0; f < slots; ++f) {
+        if (f == e || kp[f] == kCryptoFree) continue;
+        const float idf = __uint_as_float(kp[f]), wf = wp[f];
+        before += (wf > we) || (wf == we && idf < ide);
+      }
+      if (before == rank) { o.x = ide; o.y = we / tw; }
+      else if (before == rank + 1) { o.z = ide; o.w = we / tw; }
+    }
+    out[(size_t)j * w + i] = o;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_crypto_merge(uint32_t *__restrict__ key, float *__restrict__ wgt, const uint32_t *__restrict__ other_key, const float *__restrict__ other_wgt,
+               size_t n, int slots, FilterCounters *counters) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const uint32_t k = other_key[t];
+  if (k == kCryptoFree) return;
+  crypto_insert(key, wgt, slots, (unsigned)(t / (size_t)slots), __uint_as_float(k), other_wgt[t], counters);
+}
+
+cudaError_t launch_resolve_crypto(const uint32_t *key, const float *wgt, const float4 *total, int slots, int rank, int xres, int x0, int y0,
+                                  int w, int h, float4 *out, cudaStream_t stream) {
+  if (w <= 0 || h <= 0) return cudaSuccess;
+  k_resolve_crypto<<<h, 256, 0, stream>>>(key, wgt, total, slots, rank, xres, x0, y0, w, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_crypto_merge(uint32_t *key, float *wgt, const uint32_t *other_key, const float *other_wgt, size_t npx, int slots,
+                                FilterCounters *counters, cudaStream_t stream) {
+  const size_t n = npx * (size_t)slots;
+  if (n == 0) return cudaSuccess;
+  k_crypto_merge<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(key, wgt, other_key, other_wgt, n, slots, counters);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_filter_splat(int lens_kernel, const LensTable &lens, const CamConsts<float> &cam, const FilterConsts &fc,
                                 const AovSet &aovs, const SampleIO &s, const WorkItem *work, FilterCounters *counters,
                                 uint64_t sample_base, int num_sms, cudaStream_t stream) {

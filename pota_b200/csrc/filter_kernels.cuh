@@ -176,10 +176,7 @@ LB_DEV void splat_work_item(const E &ev, const CamConsts<float> &cam, const Filt
       if (__any_sync(0xffffffffu, pixel >= 0)) {
         float rgbw[3] = {1.f, 1.f, 1.f};
         if (chroma) { rgbw[0] = splat_ch == 0 ? 3.f : 0.f; rgbw[1] = splat_ch == 1 ? 3.f : 0.f; rgbw[2] = splat_ch == 2 ? 3.f : 0.f; }
-        for (int a = 0; a < fc.n_aov; ++a) {
-          const float4 v = aov_value(aovs, s, a, i, (float)samples);
-          if (pixel >= 0) add_to_buffer(aovs, a, (unsigned)pixel, v, w.add_energy, depth, weight, rgbw, sample_base + i);
-        }
+        splat_all_aovs(fc, aovs, s, i, (float)samples, pixel, w.add_energy, depth, weight, rgbw, sample_base + i, counters);
       }
     }
 

@@ -82,7 +82,17 @@ struct AovSet {
   unsigned long long *zkey;        // closest-filter depth|~sample key per pixel
   unsigned long long *zkey_debug;
   uint16_t *debug_samples;         // per-sample `samples * redistribute` of this batch (closest lentil_debug AOV only)
+  // cryptomatte AOVs (filter == LB_FILTER_CRYPTO): AOVData::crypto_hash_map as crypto_slots open-addressed
+  // slots per pixel; AOVData::crypto_total_weight lives in buffer[a][pixel].x
+  uint32_t *crypto_key[kMaxAov];     // [npx][crypto_slots] id bits, kCryptoFree = unused
+  float *crypto_wgt[kMaxAov];        // [npx][crypto_slots]
+  const float *crypto_ids[kMaxAov];  // this batch: [n][crypto_depth] ids of the depth sub-samples
+  float2 *crypto_cache[kMaxAov];     // this batch: [n][max(crypto_depth,1)] merged {id, weight} of each sample, packed,
+                                     // kCryptoFree-terminated (cryptomatte_construct_cache, lentil.h:779-811)
+  int32_t crypto_slots, crypto_depth;
 };
+constexpr uint32_t kCryptoFree = 0xFFFFFFFFu;  // a NaN bit pattern: Cryptomatte hashes are never NaN
+constexpr int kCryptoMaxDepth = 8;
 
 struct SampleIO {
   size_t n;
@@ -90,6 +100,8 @@ struct SampleIO {
   const float4 *rgba, *pos_cs, *raydir, *transmission;
   const uint32_t *flags;
   float inv_density;
+  const uint8_t *crypto_count;   // [n] or NULL
+  const float *crypto_opacity;   // [n][crypto_depth] or NULL
 };
 
 struct WorkItem {  // one redistributed source sample
@@ -102,6 +114,7 @@ struct WorkItem {  // one redistributed source sample
 struct FilterCounters {  // device-side mirror of lb_filter_stats + work queue heads
   unsigned long long samples, redistributed, splats, attempts, passthrough;
   unsigned long long newton_its;
+  unsigned long long crypto_dropped;
   unsigned int work_count, work_next;
 };
 
@@ -112,6 +125,12 @@ cudaError_t launch_filter_splat(int lens_kernel, const LensTable &lens, const Ca
                                 uint64_t sample_base, int num_sms, cudaStream_t stream);
 cudaError_t launch_closest_gather(const FilterConsts &fc, const AovSet &aovs, const SampleIO &s, uint64_t sample_base,
                                   cudaStream_t stream);
+// ranked cryptomatte resolve of one bucket (lentil_imager.cpp:122-161); out is read-modify-write
+cudaError_t launch_resolve_crypto(const uint32_t *key, const float *wgt, const float4 *total, int slots, int rank, int xres, int x0, int y0,
+                                  int w, int h, float4 *out, cudaStream_t stream);
+// multi-GPU: fold another rank's tables into this rank's
+cudaError_t launch_crypto_merge(uint32_t *key, float *wgt, const uint32_t *other_key, const float *other_wgt, size_t npx, int slots,
+                                FilterCounters *counters, cudaStream_t stream);
 cudaError_t launch_resolve(const float4 *buffer, const float *weight, int filter, int role, int xres, int x0, int y0, int w, int h,
                            float4 *out, cudaStream_t stream);
 

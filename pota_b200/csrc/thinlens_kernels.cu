@@ -296,10 +296,7 @@ k_filter_splat_thinlens(const __grid_constant__ CamConsts<float> cam, const __gr
       __syncwarp();
       const unsigned ok = __ballot_sync(0xffffffffu, pixel >= 0);
       if (ok) {
-        for (int a = 0; a < fc.n_aov; ++a) {
-          const float4 v = aov_value(aovs, s, a, i, (float)samples);
-          if (pixel >= 0) add_to_buffer(aovs, a, (unsigned)pixel, v, w.add_energy, depth, weight, rgbw, sample_base + i);
-        }
+        splat_all_aovs(fc, aovs, s, i, (float)samples, pixel, w.add_energy, depth, weight, rgbw, sample_base + i, counters);
       }
       count += __popc(ok);
       total += batch;

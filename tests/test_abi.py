@@ -2,6 +2,7 @@
 fails loudly (no CPU fallback) when asked to compute without a device."""
 import ctypes as C
 import os
+import subprocess
 import re
 
 import pytest
@@ -45,11 +46,25 @@ def test_params_default_matches_reference_defaults(product_lib):
     assert (p.vignetting_retries, p.wavelength, p.focal_length_lentil, p.lens_model) == (15, 550.0, 35.0, LENS_IDS.index("cooke__speed_panchro__1920__40mm"))
 
 
-def test_struct_sizes():
+def test_struct_sizes(tmp_path):
+    """ctypes mirrors vs the C compiler's view of include/lentil_b200.h (sizes and the offset of each last field)."""
     assert C.sizeof(abi.CameraParams) == 28 * 4
     assert C.sizeof(abi.RayIn) == 6 * 8 and C.sizeof(abi.RayOut) == 8 * 8
-    assert C.sizeof(abi.AovDesc) == 72 and C.sizeof(abi.FrameDesc) == 24
-    assert C.sizeof(abi.FilterStats) == 40
+    pairs = [("lb_camera_params", abi.CameraParams), ("lb_bokeh_image", abi.BokehImage), ("lb_camera_state", abi.CameraState),
+             ("lb_ray_in", abi.RayIn), ("lb_ray_out", abi.RayOut), ("lb_aov_desc", abi.AovDesc), ("lb_frame_desc", abi.FrameDesc),
+             ("lb_samples", abi.Samples), ("lb_filter_stats", abi.FilterStats), ("lb_lens_work", abi.LensWork)]
+    src = '#include <stdio.h>\n#include <stddef.h>\n#include "lentil_b200.h"\nint main(void){\n'
+    for cname, ct in pairs:
+        last = ct._fields_[-1][0]
+        src += f'  printf("%zu %zu\\n", sizeof({cname}), offsetof({cname}, {last}));\n'
+    src += "  return 0;\n}\n"
+    (tmp_path / "sz.c").write_text(src)
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(tmp_path / "sz.c"), "-o", str(tmp_path / "sz")], check=True)
+    out = subprocess.run([str(tmp_path / "sz")], check=True, capture_output=True, text=True).stdout.split("\n")
+    for (cname, ct), line in zip(pairs, out):
+        size, off = (int(v) for v in line.split())
+        assert C.sizeof(ct) == size, cname
+        assert getattr(ct, ct._fields_[-1][0]).offset == off, cname
 
 
 def test_no_cpu_fallback(product_lib):
