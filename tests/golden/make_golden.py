@@ -29,6 +29,12 @@ FILTER_CASES = {
     "filter_cooke50_bokeh_chromatic": (dict(lens_model=19, fstop=2.0, focus_dist=40.0, bidir_sample_mult=5, bokeh_enable_image=1, abb_chromatic=0.3),
                                        [("RGBA", 0, 1)], 0),
 }
+CRYPTO_AOVS = [("RGBA", 0, 1), ("crypto_material00", 2, 0), ("crypto_material01", 2, 0), ("crypto_object02", 2, 0)]
+CRYPTO_CASES = {
+    "crypto_takumar50_f1.4": dict(camera_type=abi.LB_CAMERA_POLYNOMIAL_OPTICS, lens_model=5, fstop=1.4, focus_dist=35.0, bidir_sample_mult=6),
+    "crypto_thinlens50_f1.4": dict(camera_type=abi.LB_CAMERA_THINLENS, focal_length_lentil=50.0, fstop=1.4, focus_dist=35.0, bidir_sample_mult=6),
+}
+CRYPTO_DEPTH, CRYPTO_SLOTS = 4, 16
 
 
 def params(**kw):
@@ -72,6 +78,23 @@ def main():
             d["weight"] = wgt
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **d)
         print(name, "energy", float(d["buffer0"][..., :3].sum()))
+    for name, kw in CRYPTO_CASES.items():
+        p = abi.CameraParams.defaults(**kw)
+        r = ref.RefCamera(p)
+        W, H, spp = 96, 54, 9
+        fr = workloads.highlight_frame(W, H, spp, r.state.tan_fov, "cpu")
+        cr = workloads.crypto_layers(fr, CRYPTO_DEPTH, [1, 2, 3])
+        crypto = dict(depth=CRYPTO_DEPTH, count=cr["count"].numpy(), opacity=cr["opacity"].numpy(), ids={a: v.numpy() for a, v in cr["ids"].items()})
+        r.filter_begin(W, H, CRYPTO_AOVS, spp=spp)
+        r.filter_accumulate(fr["px"].numpy(), fr["py"].numpy(), fr["rgba"].numpy(), fr["pos_cs"].numpy(), 1.0 / spp, crypto=crypto)
+        d = dict(params=np.frombuffer(bytes(p), np.uint8), W=W, H=H, spp=spp, depth=CRYPTO_DEPTH, aov_names=np.array([a[0] for a in CRYPTO_AOVS]))
+        for a in (1, 2, 3):
+            ids, wts, tot, mx = r.crypto(a, CRYPTO_SLOTS)
+            assert mx <= CRYPTO_SLOTS
+            d[f"ids{a}"], d[f"weights{a}"], d[f"total{a}"] = ids, wts, tot
+            d[f"resolved{a}"] = r.resolve(a, fill=-7.0)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **d)
+        print(name, "largest id table", mx)
 
 
 if __name__ == "__main__":

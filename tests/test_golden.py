@@ -17,6 +17,7 @@ GOLD = os.path.join(os.path.dirname(__file__), "golden")
 IN_KEYS = ("sx", "sy", "dsx", "dsy", "lensx", "lensy")
 RAY_FILES = sorted(glob.glob(os.path.join(GOLD, "rays_*.npz")))
 FILTER_FILES = sorted(glob.glob(os.path.join(GOLD, "filter_*.npz")))
+CRYPTO_FILES = sorted(glob.glob(os.path.join(GOLD, "crypto_*.npz")))
 
 
 def _params(g):
@@ -36,7 +37,7 @@ def _frame(g, tan_fov):
 
 
 def test_fixtures_present():
-    assert len(RAY_FILES) >= 3 and len(FILTER_FILES) >= 2
+    assert len(RAY_FILES) >= 3 and len(FILTER_FILES) >= 2 and len(CRYPTO_FILES) >= 2
 
 
 @pytest.mark.parametrize("path", RAY_FILES, ids=os.path.basename)
@@ -67,6 +68,63 @@ def test_oracle_reproduces_reference_framebuffers(path):
         np.testing.assert_array_equal(buf, g[f"buffer{a}"])
         np.testing.assert_array_equal(wgt, g["weight"])
         np.testing.assert_array_equal(cam.resolve(a), g[f"resolved{a}"])
+
+
+def _crypto_inputs(g, tan_fov):
+    W, H, spp, depth = int(g["W"]), int(g["H"]), int(g["spp"]), int(g["depth"])
+    aovs = [(str(n), 0 if str(n) == "RGBA" else 2, 1 if str(n) == "RGBA" else 0) for n in g["aov_names"]]
+    fr = workloads.highlight_frame(W, H, spp, tan_fov, "cpu")
+    cr = workloads.crypto_layers(fr, depth, [a for a in range(len(aovs)) if aovs[a][1] == 2])
+    return W, H, spp, aovs, fr, cr
+
+
+@pytest.mark.parametrize("path", CRYPTO_FILES, ids=os.path.basename)
+def test_oracle_reproduces_reference_cryptomatte(path):
+    g = np.load(path)
+    cam = orc.OracleCamera(_params(g))
+    W, H, spp, aovs, fr, cr = _crypto_inputs(g, cam.state.tan_fov)
+    cam.filter_begin(W, H, aovs)
+    cam.filter_accumulate(fr["px"].numpy(), fr["py"].numpy(), fr["rgba"].numpy(), fr["pos_cs"].numpy(), 1.0 / spp,
+                          crypto=dict(depth=cr["depth"], count=cr["count"].numpy(), opacity=cr["opacity"].numpy(), ids={a: v.numpy() for a, v in cr["ids"].items()}))
+    for a in range(1, len(aovs)):
+        ids, wts, tot, mx = cam.crypto(a, g[f"ids{a}"].shape[2])
+        np.testing.assert_array_equal(ids.view(np.uint32), g[f"ids{a}"].view(np.uint32))
+        np.testing.assert_array_equal(wts, g[f"weights{a}"])
+        np.testing.assert_array_equal(tot, g[f"total{a}"])
+        np.testing.assert_array_equal(cam.resolve(a, fill=-7.0).view(np.uint32), g[f"resolved{a}"].view(np.uint32))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", CRYPTO_FILES, ids=os.path.basename)
+def test_gpu_cryptomatte_against_reference_golden(path, kernel_kind):
+    import torch
+
+    from pota_b200.camera import Camera
+    from tests.test_crypto_gpu import _planes
+
+    g = np.load(path)
+    p = _params(g)
+    cam = Camera(p, None, device=0)
+    W, H, spp, aovs, fr, cr = _crypto_inputs(g, cam.state.tan_fov)
+    cam.filter_begin(W, H, aovs)
+    cam.filter_accumulate(fr["px"].cuda(), fr["py"].cuda(), fr["rgba"].cuda(), fr["pos_cs"].cuda(), 1.0 / spp,
+                          crypto=dict(depth=cr["depth"], count=cr["count"].cuda(), opacity=cr["opacity"].cuda(), ids={a: v.cuda() for a, v in cr["ids"].items()}))
+    torch.cuda.synchronize()
+    assert cam.filter_stats()["crypto_dropped"] == 0
+    exact = p.camera_type == abi.LB_CAMERA_THINLENS  # FP32 thin-lens splat positions are the reference's own
+    for a in range(1, len(aovs)):
+        palette = np.union1d(np.unique(cr["ids"][a].numpy()), np.float32([0.0]))
+        ids, wts, tot = cam.crypto(a)
+        pg, ng = _planes(ids, wts, palette)
+        po, no = _planes(g[f"ids{a}"], g[f"weights{a}"], palette)
+        assert (ng == no).mean() >= (1.0 if exact else 0.98)
+        for k in range(len(palette)):
+            if po[k].sum() > 0:
+                assert np.abs(pg[k] - po[k]).sum() / po[k].sum() <= (1e-5 if exact else 5e-3), (aovs[a][0], palette[k])
+        np.testing.assert_allclose(tot.sum(dtype=np.float64), g[f"total{a}"].sum(dtype=np.float64), rtol=1e-5)
+        ro, rg = g[f"resolved{a}"], cam.resolve(a, fill=-7.0).cpu().numpy()
+        agree = (ro[..., 0] == rg[..., 0]) & (np.abs(ro[..., 1] - rg[..., 1]) <= 2e-3)
+        assert agree.mean() > (0.999 if exact else 0.97), agree.mean()
 
 
 @pytest.mark.gpu
