@@ -189,6 +189,7 @@ def main():
     ap.add_argument("--skip-splat", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-thinlens", action="store_true")
+    ap.add_argument("--skip-crypto", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -335,6 +336,10 @@ def main():
     if not args.skip_thinlens:
         thin = bench_thinlens(args, rank, world, local_rank, dev, barrier, max_over_ranks, sum_over_ranks, hbm_peak)
 
+    crypto = None
+    if not args.skip_crypto:
+        crypto = bench_crypto(args, rank, world, local_rank, dev, barrier, max_over_ranks, sum_over_ranks)
+
     if rank == 0:
         line = {
             "metric": "camera_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -349,7 +354,7 @@ def main():
                                                      "sample": f"{CPU_SAMPLE_PER_THREAD * (os.cpu_count() or 1)} rays on a coarser 16:9 pixel grid covering the same sensor, all host threads; "
                                                                + ("reference = /root/reference/src compiled behind oracle/shims (oracle/_ref)" if cpu["kind"] == "reference"
                                                                   else "port = oracle/lentil_oracle.cpp (FP64 restatement)")},
-            "splat": splat, "thinlens": thin,
+            "splat": splat, "thinlens": thin, "cryptomatte": crypto,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -487,6 +492,64 @@ def bench_thinlens(args, rank, world, local_rank, dev, barrier, max_over_ranks, 
                                    "frac": adds * 20.0 / s2 / 1e9 / world / max(red_peak.value, 1e-9)}},
             "config": {"workload": f"ThinLens camera_type, focal 50 mm: rays {FRAME_W}x{FRAME_H}x{spp}spp per GPU f/2.8 focus 150; "
                                    f"splats {SPLAT_W}x{SPLAT_H}x{sspp}spp highlight frame f/1.4 focus 35, 250x250 image-bokeh kernel"}}
+
+
+def bench_crypto(args, rank, world, local_rank, dev, barrier, max_over_ranks, sum_over_ranks):
+    """Cryptomatte redistribution on the thin-lens splat frame: RGBA + 3 ranked cryptomatte AOVs
+    with 4 depth sub-samples per sample, against the same frame with RGBA alone.  The extra cost is table traffic:
+    per splat and cryptomatte AOV one scalar reduction (crypto_total_weight) plus, per cached id, one slot probe
+    (4 B read or compare-and-swap) and one scalar reduction (4 B)."""
+    import torch
+
+    from pota_b200.camera import Camera
+
+    sspp = max(1, int(round(SPLAT_SPP * args.frame_scale)))
+    p = abi.CameraParams.defaults(camera_type=abi.LB_CAMERA_THINLENS, fstop=1.4, focus_dist=35.0, focal_length_lentil=50.0, bidir_sample_mult=10,
+                                  bokeh_enable_image=1)
+    cam = Camera(p, bokeh=workloads.disc_bokeh_image(250), device=local_rank)
+    total = SPLAT_W * SPLAT_H * sspp
+    lo, hi = total * rank // world, total * (rank + 1) // world
+    fr = workloads.highlight_frame(SPLAT_W, SPLAT_H, sspp, cam.state.tan_fov, dev, lo, hi - lo, grid=SPLAT_GRID)
+    depth = 4
+    aov_sets = {"rgba_only": [("RGBA", abi.LB_FILTER_GAUSSIAN, abi.LB_AOV_RGBA)],
+                "rgba_plus_3_crypto": [("RGBA", abi.LB_FILTER_GAUSSIAN, abi.LB_AOV_RGBA), ("crypto_material00", abi.LB_FILTER_CRYPTO, 0),
+                                       ("crypto_object00", abi.LB_FILTER_CRYPTO, 0), ("crypto_asset00", abi.LB_FILTER_CRYPTO, 0)]}
+    cr = workloads.crypto_layers(fr, depth, [1, 2, 3], cell=64)
+    crypto = dict(depth=depth, count=cr["count"], opacity=cr["opacity"], ids=cr["ids"])
+    stream = torch.cuda.current_stream()
+    steps = max(1, min(args.steps, 3))
+    out = {}
+    for name, aovs in aov_sets.items():
+        def step():
+            cam.filter_begin(SPLAT_W, SPLAT_H, aovs)
+            cam.filter_accumulate(fr["px"], fr["py"], fr["rgba"], fr["pos_cs"], 1.0 / sspp, stream=stream, crypto=crypto if len(aovs) > 1 else None)
+
+        step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            step()
+        e1.record(stream)
+        barrier()
+        s = max_over_ranks(e0.elapsed_time(e1) * 1e-3) / steps
+        st = cam.filter_stats()
+        splats = sum_over_ranks(float(st["splats"]))
+        out[name] = {"value": splats / s, "unit": "splats/s", "ms_per_step": s * 1e3, "splats_per_step": splats,
+                     "crypto_dropped": sum_over_ranks(float(st["crypto_dropped"]))}
+    res = None
+    if len(aov_sets["rgba_plus_3_crypto"]) > 1:
+        res_t0, res_t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        res_t0.record(stream)
+        img = cam.resolve(1, stream=stream)
+        res_t1.record(stream)
+        torch.cuda.synchronize()
+        res = {"ms": res_t0.elapsed_time(res_t1), "pixels": SPLAT_W * SPLAT_H, "mean_rank0_coverage": float(img[..., 1].mean().item())}
+    out["slowdown"] = out["rgba_only"]["value"] / max(out["rgba_plus_3_crypto"]["value"], 1e-9)
+    out["ranked_resolve"] = res
+    out["config"] = {"workload": f"ThinLens splats {SPLAT_W}x{SPLAT_H}x{sspp}spp highlight frame f/1.4 focus 35, 250x250 image-bokeh kernel; "
+                                 f"3 cryptomatte AOVs, {depth} depth sub-samples per sample, 16 id slots per pixel, ids constant over 64x64 pixel blocks"}
+    return out
 
 
 if __name__ == "__main__":

@@ -3,7 +3,7 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/multi_gpu_check.py
 
 Every rank accumulates its sample range of one frame; after the NCCL combine rank 0 must hold the same
-framebuffers (gaussian AOVs, weight, closest AOV) as a single-GPU run over all samples.
+framebuffers (gaussian AOVs, weight, closest AOV, cryptomatte id tables) as a single-GPU run over all samples.
 """
 import os
 import sys
@@ -23,15 +23,21 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     p = abi.CameraParams.defaults(camera_type=1, lens_model=5, fstop=1.4, focus_dist=35.0, bidir_sample_mult=6)
     W, H, spp = 320, 180, 4
-    aovs = [("RGBA", 0, 1), ("light0", 0, 0), ("N", 1, 0)]
+    aovs = [("RGBA", 0, 1), ("light0", 0, 0), ("N", 1, 0), ("crypto_material00", 2, 0), ("crypto_object01", 2, 0)]
     total = W * H * spp
 
     def run(cam, lo, hi, dev):
         fr = workloads.highlight_frame(W, H, spp, cam.state.tan_fov, dev, lo, hi - lo, n_extra_aov=2)
         cam.filter_begin(W, H, aovs)
         cam.filter_set_sample_base(lo)
-        cam.filter_accumulate(fr["px"], fr["py"], fr["rgba"], fr["pos_cs"], 1.0 / spp, aov_values=[None, fr["aov_values"][0], fr["aov_values"][1]])
-        return fr
+        # crypto layers are generated for the whole frame so that every rank sees the single-GPU run's values
+        full = workloads.highlight_frame(W, H, spp, cam.state.tan_fov, dev)
+        cr = workloads.crypto_layers(full, 3, [3, 4])
+        crypto = dict(depth=3, count=cr["count"][lo:hi].contiguous(), opacity=cr["opacity"][lo:hi].contiguous(),
+                      ids={a: v[lo:hi].contiguous() for a, v in cr["ids"].items()})
+        cam.filter_accumulate(fr["px"], fr["py"], fr["rgba"], fr["pos_cs"], 1.0 / spp,
+                              aov_values=[None, fr["aov_values"][0], fr["aov_values"][1], None, None], crypto=crypto)
+        return fr, crypto
 
     dev = torch.device("cuda", local)
     cam = Camera(p, device=local)
@@ -55,9 +61,20 @@ def main():
                 if flt == 0:
                     np.testing.assert_allclose(got, ref, rtol=2e-5, atol=2e-5, err_msg=f"root={root} {name}")
                     np.testing.assert_allclose(gw, rw, rtol=2e-5, atol=1e-6)
+                elif flt == 2:
+                    # same {id -> weight} table per pixel (slot positions may differ), same crypto_total_weight
+                    np.testing.assert_allclose(got[..., 0], ref[..., 0], rtol=2e-5, atol=1e-6, err_msg=f"root={root} total weight {name}")
+                    ig, wg, _ = cam.crypto(a)
+                    ir, wr, _ = single.crypto(a)
+                    og, orr = np.argsort(ig.view(np.uint32), axis=2), np.argsort(ir.view(np.uint32), axis=2)
+                    np.testing.assert_array_equal(np.take_along_axis(ig.view(np.uint32), og, 2), np.take_along_axis(ir.view(np.uint32), orr, 2))
+                    np.testing.assert_allclose(np.take_along_axis(wg, og, 2), np.take_along_axis(wr, orr, 2), rtol=2e-5, atol=1e-6)
+                    rg, rr = cam.resolve(a, fill=-7.0).cpu().numpy(), single.resolve(a, fill=-7.0).cpu().numpy()
+                    assert ((rg[..., 0] == rr[..., 0]) & (np.abs(rg[..., 1] - rr[..., 1]) < 1e-4)).mean() > 0.999
                 else:
                     assert (np.abs(got - ref).max(axis=2) > 1e-6).mean() < 1e-3, f"root={root} closest {name}"
             assert cam.filter_stats()["samples"] == hi - lo  # (a rank whose slice holds no highlight has 0 splats)
+            assert cam.filter_stats()["crypto_dropped"] == 0
     dist.barrier()
     cam.comm_destroy()
     if rank == 0:
