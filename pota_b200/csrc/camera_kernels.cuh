@@ -111,4 +111,178 @@ LB_DEV void camera_create_ray(const E &ev, const CamConsts<float> &cam, const Ra
   if (io.tries) io.tries[i] = tries;
 }
 
+// ---- two rays per thread: the polynomials run on the packed FP32 instructions of sm_100a ----------------------
+// K1 is issue-bound, not FMA-pipe-bound (ncu r01: issue slots 80 % busy, FMA pipe 65 %): FFMA2/FMUL2/FADD2 carry two
+// independent FP32 lanes per issued instruction, so evaluating the SAME polynomial body for two rays at once halves
+// the issue slots of the polynomial code while every half stays bit-identical to the scalar body.  A thread owns
+// rays j and j + ceil(n/2) (both halves' loads and stores stay fully coalesced) and walks their three traces in
+// lockstep; whatever is not polynomial runs once per half as before.
+LB_DEV float lo_hi(const float2 &v, int h) { return h ? v.y : v.x; }
+
+// pt_sample_aperture for two traces in lockstep; a half that has converged (or is off) is no longer updated
+template <typename E>
+LB_DEV void pt_sample_aperture2(const E &ev, const float x[2], const float y[2], float dx[2], float dy[2], float lambda,
+                                const float ax[2], const float ay[2], float dist, const bool on[2]) {
+  float sqr_err[2] = {on[0] ? 3.402823466e+38f : 0.f, on[1] ? 3.402823466e+38f : 0.f};
+  for (int k = 0; k < 5 && (sqr_err[0] > 1e-4f || sqr_err[1] > 1e-4f); k++) {
+    float2 b[5];
+    b[0] = make_float2(x[0] + dist * dx[0], x[1] + dist * dx[1]);
+    b[1] = make_float2(y[0] + dist * dy[0], y[1] + dist * dy[1]);
+    b[2] = make_float2(dx[0], dx[1]);
+    b[3] = make_float2(dy[0], dy[1]);
+    b[4] = make_float2(lambda, lambda);
+    float2 ap[2], J[4];
+    ev.ap_jac2(b, ap, J);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (!(sqr_err[h] > 1e-4f)) continue;
+      const float J0 = lo_hi(J[0], h), J1 = lo_hi(J[1], h), J2 = lo_hi(J[2], h), J3 = lo_hi(J[3], h);
+      const float invdet = 1.0f / (J0 * J3 - J1 * J2);
+      const float e0 = ax[h] - lo_hi(ap[0], h), e1 = ay[h] - lo_hi(ap[1], h);
+      dx[h] += (J3 * invdet) * e0;
+      dx[h] += (-J1 * invdet) * e1;
+      dy[h] += (-J2 * invdet) * e0;
+      dy[h] += (J0 * invdet) * e1;
+      sqr_err[h] = e0 * e0 + e1 * e1;
+    }
+  }
+}
+
+struct FwRay2 {
+  float o[3][2], d[3][2];
+  bool ok[2];
+};
+
+// Camera::trace_ray_fw_po (lentil.h:283-427) for two rays in lockstep.  `u` carries the aperture sample of each half:
+// the main trace writes it, the derivative traces reuse it (they are called with the same r1, r2: lentil_camera.cpp:111-112).
+// A derivative trace that fails would repeat identical work vignetting_retries times (lentil.h:296,313): one pass suffices.
+template <typename E>
+LB_DEV void trace_pair_fw_po(const E &ev, const CamConsts<float> &cam, const float sx[2], const float sy[2], float r1[2], float r2[2],
+                             float ux[2], float uy[2], bool deriv_ray, const uint32_t ray_id[2], const bool valid[2], FwRay2 &r,
+                             int tries[2]) {
+  bool active[2] = {valid[0], valid[1]};
+  bool success[2] = {false, false};
+  float out[4][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+  tries[0] = tries[1] = 0;
+  while (active[0] || active[1]) {
+    float x[2], y[2], dx[2] = {0.f, 0.f}, dy[2] = {0.f, 0.f}, ax[2], ay[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      x[h] = sx[h] * cam.sensor_half;
+      y[h] = sy[h] * cam.sensor_half;
+      if (active[h] && cam.enable_dof && !deriv_ray) {
+        if (tries[h] > 0) {  // retry lens sample: counter RNG instead of the global xor128 (lentil.h:313-316)
+          uint32_t seed = tea8(ray_id[h], (uint32_t)tries[h]);
+          r1[h] = lcg_rng(seed);
+          r2[h] = lcg_rng(seed);
+        }
+        if (cam.bokeh_n > 0) bokeh_sample(cam, r1[h], r2[h], ux[h], uy[h]);
+        else if (cam.blades < 2) concentric_disk_sample(r1[h], r2[h], ux[h], uy[h]);
+        else sample_triangular_aperture(ux[h], uy[h], r1[h], r2[h], 1.0f, cam.blades);
+      }
+      ax[h] = ux[h] * cam.aperture_radius;
+      ay[h] = uy[h] * cam.aperture_radius;
+    }
+    if (cam.enable_dof) pt_sample_aperture2(ev, x, y, dx, dy, cam.lambda, ax, ay, cam.sensor_shift, active);
+    float2 b[5], o2[4], t2;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      x[h] += dx[h] * cam.sensor_shift;  // move to beginning of polynomial (lentil.h:349-350)
+      y[h] += dy[h] * cam.sensor_shift;
+    }
+    b[0] = make_float2(x[0], x[1]);
+    b[1] = make_float2(y[0], y[1]);
+    b[2] = make_float2(dx[0], dx[1]);
+    b[3] = make_float2(dy[0], dy[1]);
+    b[4] = make_float2(cam.lambda, cam.lambda);
+    ev.out5_2(b, o2, t2);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (!active[h]) continue;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) out[k][h] = lo_hi(o2[k], h);
+      const float transmittance = fmaxf(0.f, lo_hi(t2, h));
+      const float px = x[h] + dx[h] * cam.bfl, py = y[h] + dy[h] * cam.bfl;
+      const bool fail = transmittance <= 0.f || out[0][h] * out[0][h] + out[1][h] * out[1][h] > cam.outer_pupil_r2 ||
+                        px * px + py * py > cam.inner_pupil_r2;
+      if (!fail) { success[h] = true; active[h] = false; }
+      else { ++tries[h]; if (deriv_ray || tries[h] > cam.vignetting_retries) active[h] = false; }
+    }
+  }
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const float o4[4] = {out[0][h], out[1][h], out[2][h], out[3][h]};
+    float pos[3], dir[3];
+    outer_to_cs(cam, o4, pos, dir);
+    float o[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { o[k] = pos[k] * cam.unit_scale; dir[k] *= cam.unit_scale; }
+    const float len = sqrtf(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
+    const float inv = len != 0.f ? 1.0f / len : 0.f;
+    bool ok = success[h];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      r.o[k][h] = o[k];
+      r.d[k][h] = dir[k] * inv;
+      if (r.o[k][h] != r.o[k][h] || r.d[k][h] != r.d[k][h]) ok = false;  // NaN bailout (lentil.h:421-425)
+    }
+    r.ok[h] = ok;
+  }
+}
+
+// camera_create_ray (lentil_camera.cpp:78-125) for rays j and j + ceil(n/2)
+template <typename E>
+LB_DEV void camera_create_ray_pair(const E &ev, const CamConsts<float> &cam, const RayIO &io, size_t j, size_t n, uint64_t ray_id_base) {
+  const size_t half = (n + 1) / 2;
+  const size_t i[2] = {j, j + half};
+  const bool valid[2] = {true, i[1] < n};
+  float sx[2], sy[2], dsx[2], dsy[2], r1[2], r2[2], ux[2] = {0.f, 0.f}, uy[2] = {0.f, 0.f};
+  uint32_t ray_id[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const size_t k = valid[h] ? i[h] : i[0];
+    sx[h] = __ldg(io.sx + k); sy[h] = __ldg(io.sy + k);
+    dsx[h] = __ldg(io.dsx + k); dsy[h] = __ldg(io.dsy + k);
+    r1[h] = __ldg(io.lensx + k); r2[h] = __ldg(io.lensy + k);
+    ray_id[h] = (uint32_t)(ray_id_base + k);
+  }
+  const float step = 0.001f;
+  const float fd = step * cam.deriv_baseline;
+  const float inv_fd = 1.0f / fd;
+  const size_t P = io.plane;
+  float mo[3][2], md[3][2];
+  // main rays, then the two pairs of differential rays, through ONE copy of the packed trace code
+#pragma unroll 1
+  for (int t = 0; t < 3; ++t) {
+    float tsx[2], tsy[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      tsx[h] = t == 1 ? sx[h] + (dsx[h] * fd) : sx[h];
+      tsy[h] = t == 2 ? sy[h] + (dsy[h] * fd) : sy[h];
+    }
+    FwRay2 r;
+    int tr[2];
+    trace_pair_fw_po(ev, cam, tsx, tsy, r1, r2, ux, uy, t != 0, ray_id, valid, r, tr);
+    float *po = t == 0 ? io.origin : (t == 1 ? io.dOdx : io.dOdy);
+    float *pd = t == 0 ? io.dir : (t == 1 ? io.dDdx : io.dDdy);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (!valid[h]) continue;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        if (t == 0) {
+          mo[k][h] = r.o[k][h]; md[k][h] = r.d[k][h];
+          if (po) po[k * P + i[h]] = r.o[k][h];
+          if (pd) pd[k * P + i[h]] = r.d[k][h];
+          if (io.weight) io.weight[k * P + i[h]] = r.ok[h] ? cam.exposure : 0.f * cam.exposure;
+        } else {
+          if (po) po[k * P + i[h]] = (r.o[k][h] - mo[k][h]) * inv_fd;
+          if (pd) pd[k * P + i[h]] = (r.d[k][h] - md[k][h]) * inv_fd;
+        }
+      }
+      if (t == 0 && io.tries) io.tries[i[h]] = tr[h];
+    }
+  }
+}
+
 }  // namespace lb

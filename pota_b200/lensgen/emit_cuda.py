@@ -27,9 +27,10 @@ def _fmt(c: float) -> str:
 class Dag:
     """Greedy multiplication DAG over exponent tuples."""
 
-    def __init__(self, lines, prefix):
+    def __init__(self, lines, prefix, packed=False):
         self.lines = lines
         self.prefix = prefix
+        self.packed = packed
         self.avail = {}
         self.count = 0
         self.muls = 0
@@ -61,15 +62,95 @@ class Dag:
         name = "%s%d" % (self.prefix, self.count)
         self.count += 1
         self.muls += 1
-        self.lines.append("    const float %s = %s * %s;" % (name, self.avail[a], self.avail[r]))
+        if self.packed:
+            self.lines.append("    const float2 %s = __fmul2_rn(%s, %s);" % (name, self.avail[a], self.avail[r]))
+        else:
+            self.lines.append("    const float %s = %s * %s;" % (name, self.avail[a], self.avail[r]))
         self.avail[m] = name
         return name
 
 
-def emit_group(name, signature, polys, outputs):
-    """One device function evaluating `polys` (list of term lists) at point b, writing `outputs` (lvalues)."""
-    lines = ["  LB_DEV void %s(%s) const {" % (name, signature), "    const float b0 = b[0], b1 = b[1], b2 = b[2], b3 = b[3], b4 = b[4];"]
-    dag = Dag(lines, "m")
+def _c2(c: float) -> str:
+    return "make_float2(%s, %s)" % (_fmt(c), _fmt(c))  # folds to the broadcast-immediate operand of FFMA2/FMUL2
+
+
+# Order in which the packed bodies form and consume their monomials.  Measured on lens 5 (K1, registers / spill bytes at
+# 4 blocks per SM): grouped (all monomials, then all sums) 202 / 248, degree-sorted streaming 164 / 200,
+# lexicographic streaming 154 / 40 -- exponent-tuple order finishes whole sub-trees of the multiplication DAG early.
+PACKED_ORDER = os.environ.get("LB_PACKED_ORDER", "lex")  # grouped | degree | lex
+
+
+def _emit_streamed(lines, polys, outputs):
+    """Packed body with every monomial consumed right after it is formed (short live ranges: the packed values take
+    two registers each).  Accumulation order per polynomial therefore follows the monomial order, not the term order."""
+    key = (lambda t: (sum(t), t)) if PACKED_ORDER == "degree" else (lambda t: t)
+    monos = sorted({tuple(e) for terms in polys for _, e in terms if sum(e) > 0}, key=key)
+    uses = {}
+    for j, terms in enumerate(polys):
+        for c, e in terms:
+            if sum(e) > 0:
+                uses.setdefault(tuple(e), []).append((j, c))
+    consts = [sum(c for c, e in terms if sum(e) == 0) for terms in polys]
+    nterms = [sum(1 for c, e in terms if sum(e) > 0) for terms in polys]
+    n_acc = [2 if n >= 12 else 1 for n in nterms]
+    started = [[False, False] for _ in polys]
+    count = [0] * len(polys)
+    names = [out.replace("[", "").replace("]", "").replace("*", "") for out in outputs]
+    ffma = 0
+
+    def consume(m, var):
+        nonlocal ffma
+        for j, c in uses.get(m, []):
+            k = count[j] % n_acc[j]
+            count[j] += 1
+            acc = "%s_%d" % (names[j], k)
+            if not started[j][k]:
+                started[j][k] = True
+                if k == 0 and consts[j] != 0.0:
+                    lines.append("    float2 %s = __ffma2_rn(%s, %s, %s);" % (acc, _c2(c), var, _c2(consts[j])))
+                else:
+                    lines.append("    float2 %s = __fmul2_rn(%s, %s);" % (acc, _c2(c), var))
+            else:
+                lines.append("    %s = __ffma2_rn(%s, %s, %s);" % (acc, _c2(c), var, acc))
+            ffma += 1
+
+    body = []
+    dag = Dag(body, "m", True)
+    for i in range(5):
+        t = [0] * 5
+        t[i] = 1
+        consume(tuple(t), VARS[i])
+    for m in monos:
+        if sum(m) == 1:
+            continue
+        before = len(body)
+        var = dag.get(m)
+        lines.extend(body[before:])
+        consume(m, var)
+        # intermediates created on the way may be monomials of the group as well: they are consumed when their turn comes
+    for j, out in enumerate(outputs):
+        accs = ["%s_%d" % (names[j], k) for k in range(2) if started[j][k]]
+        if not accs:
+            lines.append("    %s = %s;" % (out, _c2(consts[j])))
+        elif len(accs) == 1:
+            lines.append("    %s = %s;" % (out, accs[0]))
+        else:
+            lines.append("    %s = __fadd2_rn(%s, %s);" % (out, accs[0], accs[1]))
+    lines.append("  }")
+    return lines, dag.muls, ffma
+
+
+def emit_group(name, signature, polys, outputs, packed=False):
+    """One device function evaluating `polys` (list of term lists) at point b, writing `outputs` (lvalues).
+
+    packed: every value is a float2 holding the same quantity of TWO independent evaluation points, every operation the
+    packed FP32 instruction of sm_100a (FMUL2 / FFMA2 / FADD2 through __fmul2_rn / __ffma2_rn / __fadd2_rn) in the same
+    order as the scalar body, so each half is bit-identical to the scalar result at half the issue slots."""
+    ty = "float2" if packed else "float"
+    lines = ["  LB_DEV void %s(%s) const {" % (name, signature), "    const %s b0 = b[0], b1 = b[1], b2 = b[2], b3 = b[3], b4 = b[4];" % ty]
+    if packed and PACKED_ORDER != "grouped":
+        return _emit_streamed(lines, polys, outputs)
+    dag = Dag(lines, "m", packed)
     monos = sorted({tuple(e) for terms in polys for _, e in terms if sum(e) > 0}, key=lambda t: (sum(t), t))
     for m in monos:
         dag.get(m)
@@ -86,18 +167,29 @@ def emit_group(name, signature, polys, outputs):
                 continue
             var = "%s_%d" % (out.replace("[", "").replace("]", "").replace("*", ""), k)
             c0, e0 = part[0]
-            if k == 0 and const != 0.0:
+            if packed:
+                if k == 0 and const != 0.0:
+                    lines.append("    float2 %s = __ffma2_rn(%s, %s, %s);" % (var, _c2(c0), dag.avail[e0], _c2(const)))
+                else:
+                    lines.append("    float2 %s = __fmul2_rn(%s, %s);" % (var, _c2(c0), dag.avail[e0]))
+                for c, e in part[1:]:
+                    lines.append("    %s = __ffma2_rn(%s, %s, %s);" % (var, _c2(c), dag.avail[e], var))
+            elif k == 0 and const != 0.0:
                 lines.append("    float %s = fmaf(%s, %s, %s);" % (var, _fmt(c0), dag.avail[e0], _fmt(const)))
+                for c, e in part[1:]:
+                    lines.append("    %s = fmaf(%s, %s, %s);" % (var, _fmt(c), dag.avail[e], var))
             else:
                 lines.append("    float %s = %s * %s;" % (var, _fmt(c0), dag.avail[e0]))
-            for c, e in part[1:]:
-                lines.append("    %s = fmaf(%s, %s, %s);" % (var, _fmt(c), dag.avail[e], var))
+                for c, e in part[1:]:
+                    lines.append("    %s = fmaf(%s, %s, %s);" % (var, _fmt(c), dag.avail[e], var))
             ffma += len(part)
             acc.append(var)
         if not acc:
-            lines.append("    %s = %s;" % (out, _fmt(const)))
+            lines.append("    %s = %s;" % (out, _c2(const) if packed else _fmt(const)))
         elif len(acc) == 1:
             lines.append("    %s = %s;" % (out, acc[0]))
+        elif packed:
+            lines.append("    %s = __fadd2_rn(%s, %s);" % (out, acc[0], acc[1]))
         else:
             lines.append("    %s = %s + %s;" % (out, acc[0], acc[1]))
     lines.append("  }")
@@ -125,6 +217,12 @@ def lens_unit(lens) -> tuple[str, dict]:
                                  ["out[0]", "out[1]", "out[2]", "out[3]", "T"])
     src += body
     stats["out5"] = (mul, ffma)
+    body, _, _ = emit_group("ap_jac2", "const float2 b[5], float2 ap[2], float2 J[4]", [P["ap_x"], P["ap_y"]] + dap,
+                            ["ap[0]", "ap[1]", "J[0]", "J[1]", "J[2]", "J[3]"], packed=True)
+    src += body
+    body, _, _ = emit_group("out5_2", "const float2 b[5], float2 out[4], float2 &T", [P["out_x"], P["out_y"], P["out_dx"], P["out_dy"], P["out_t"]],
+                            ["out[0]", "out[1]", "out[2]", "out[3]", "T"], packed=True)
+    src += body
     body, mul, ffma = emit_group("transmittance_", "const float b[5], float &T", [P["out_t"]], ["T"])
     src += body
     src += ["  LB_DEV float transmittance(const float b[5]) const { float T; transmittance_(b, T); return T; }"]
@@ -137,9 +235,9 @@ def lens_unit(lens) -> tuple[str, dict]:
     src += ["};", "",
             "__global__ void __launch_bounds__(128%s)" % K1_MIN_BLOCKS,
             "k_create_rays_%d(const __grid_constant__ CamConsts<float> cam, const __grid_constant__ RayIO io, size_t n, uint64_t ray_id_base) {" % k,
-            "  const size_t i = (size_t)blockIdx.x * 128 + threadIdx.x;",
-            "  if (i >= n) return;",
-            "  camera_create_ray(Eval%d{}, cam, io, i, ray_id_base);" % k,
+            "  const size_t j = (size_t)blockIdx.x * 128 + threadIdx.x;  // rays j and j + ceil(n/2)",
+            "  if (j >= (n + 1) / 2) return;",
+            "  camera_create_ray_pair(Eval%d{}, cam, io, j, n, ray_id_base);" % k,
             "}", "",
             "__global__ void __launch_bounds__(128%s)" % K2_MIN_BLOCKS,
             "k_filter_splat_%d(const __grid_constant__ CamConsts<float> cam, const __grid_constant__ FilterConsts fc, const __grid_constant__ AovSet aovs," % k,
@@ -147,7 +245,7 @@ def lens_unit(lens) -> tuple[str, dict]:
             "  splat_persistent(Eval%d{}, cam, fc, aovs, s, work, counters, sample_base);" % k,
             "}", "", "}  // namespace", "",
             "cudaError_t launch_fw_lens_%d(const CamConsts<float> &cam, const RayIO &io, size_t n, uint64_t ray_id_base, cudaStream_t stream) {" % k,
-            "  k_create_rays_%d<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(cam, io, n, ray_id_base);" % k,
+            "  k_create_rays_%d<<<(unsigned)(((n + 1) / 2 + 127) / 128), 128, 0, stream>>>(cam, io, n, ray_id_base);" % k,
             "  return cudaGetLastError();", "}",
             "cudaError_t launch_bw_lens_%d(const CamConsts<float> &cam, const FilterConsts &fc, const AovSet &aovs, const SampleIO &s, const WorkItem *work," % k,
             "                             FilterCounters *counters, uint64_t sample_base, int grid, cudaStream_t stream) {",
@@ -157,9 +255,11 @@ def lens_unit(lens) -> tuple[str, dict]:
 
 
 # tuning knobs: resident blocks per SM the register allocator must allow ("" = compiler's choice).
-# Measured on B200 (lens 5, C2/C3): K1 is issue-bound and flat from 3 to 5 blocks (116 -> 96 registers);
-# K2 gains 6.7 % at 4 blocks (154 -> 128 registers, no spills) and loses it again at 5 (96, spills).
-K1_MIN_BLOCKS = (", " + os.environ["LB_K1_MINBLOCKS"]) if os.environ.get("LB_K1_MINBLOCKS") else ""
+# Measured on B200 (lens 5, C2/C3): the scalar K1 was issue-bound and flat from 3 to 5 blocks (116 -> 96 registers); the
+# packed two-rays-per-thread K1 is FMA-pipe/latency-bound and wants warps: 4.94e9 rays/s at 3 blocks (156 registers),
+# 5.24e9 at 4 (128 registers, 8 bytes of spill).  K2 gains 6.7 % at 4 blocks (154 -> 128 registers, no spills) and loses
+# it again at 5 (96, spills).
+K1_MIN_BLOCKS = ", " + os.environ.get("LB_K1_MINBLOCKS", "4")
 K2_MIN_BLOCKS = ", " + os.environ.get("LB_K2_MINBLOCKS", "4")
 
 

@@ -33,14 +33,16 @@ def test_pack_is_complete_and_float32_exact():
 
 def _run_group(lines, b):
     """Execute one emitted device function body (C statements) as numpy float64 Python."""
-    env = {"fmaf": lambda a, x, y: a * x + y, "b": b}
+    env = {"fmaf": lambda a, x, y: a * x + y, "b": b,
+           # packed bodies: both halves carry the same numpy vector here
+           "make_float2": lambda a, b_: a, "__fmul2_rn": lambda a, x: a * x, "__ffma2_rn": lambda a, x, y: a * x + y, "__fadd2_rn": lambda a, x: a + x}
     out = {"ap": [None] * 2, "J": [None] * 4, "out": [None] * 4, "K": [None] * 4}
     env.update(out)
     for ln in lines:
         ln = ln.strip()
         if not ln or ln.startswith("LB_DEV") or ln == "}":
             continue
-        ln = re.sub(r"^(const )?float ", "", ln).rstrip(";")
+        ln = re.sub(r"^(const )?float2? ", "", ln).rstrip(";")
         ln = re.sub(r"(\d)f\b", r"\1", ln)  # 1.5f -> 1.5
         if ln.startswith("b0 = "):
             for k in range(5):
@@ -69,6 +71,17 @@ def test_emitted_code_matches_direct_evaluation(lens_index):
         np.testing.assert_allclose(g, want, rtol=1e-6, atol=1e-7)  # coefficients are printed with 9 significant digits (float32 literals)
     assert ffma == sum(len([1 for c, e in t if sum(e) > 0]) for t in polys)
     assert muls < 1.6 * ffma  # the DAG shares monomials across the 14 polynomials
+    # the packed (FFMA2) bodies of the forward kernel: same polynomials, monomials consumed as they are formed
+    for order in ("lex", "degree", "grouped"):
+        emit_cuda.PACKED_ORDER = order
+        try:
+            lines, muls2, ffma2 = emit_cuda.emit_group("ap_jac2", "...", polys[:6], outs[:6], packed=True)
+        finally:
+            emit_cuda.PACKED_ORDER = "lex"
+        env = _run_group(lines[1:], [X[k] for k in range(5)])
+        for terms, g in zip(polys[:6], [env["ap"][0], env["ap"][1]] + env["J"]):
+            np.testing.assert_allclose(g, poly_eval(terms, X), rtol=1e-6, atol=1e-7)
+        assert ffma2 == sum(len([1 for c, e in t if sum(e) > 0]) for t in polys[:6])
 
 
 def test_upstream_headers_are_emitted_for_every_lens(tmp_path):
