@@ -78,12 +78,19 @@ def _c2(c: float) -> str:
 # 4 blocks per SM): grouped (all monomials, then all sums) 202 / 248, degree-sorted streaming 164 / 200,
 # lexicographic streaming 154 / 40 -- exponent-tuple order finishes whole sub-trees of the multiplication DAG early.
 PACKED_ORDER = os.environ.get("LB_PACKED_ORDER", "lex")  # grouped | degree | lex
+# same choice for the scalar bodies (K2's lt_all: 154 registers grouped, 137 lex; at 5 blocks per SM 96 registers with
+# 96 bytes of spill grouped, none lex)
+SCALAR_ORDER = os.environ.get("LB_SCALAR_ORDER", "lex")
 
 
-def _emit_streamed(lines, polys, outputs):
-    """Packed body with every monomial consumed right after it is formed (short live ranges: the packed values take
-    two registers each).  Accumulation order per polynomial therefore follows the monomial order, not the term order."""
-    key = (lambda t: (sum(t), t)) if PACKED_ORDER == "degree" else (lambda t: t)
+def _emit_streamed(lines, polys, outputs, packed=True, order=None):
+    """Body with every monomial consumed right after it is formed (short live ranges: the packed values take two
+    registers each).  Accumulation order per polynomial therefore follows the monomial order, not the term order."""
+    order = order or PACKED_ORDER
+    key = (lambda t: (sum(t), t)) if order == "degree" else (lambda t: t)
+    ty = "float2" if packed else "float"
+    cst = _c2 if packed else _fmt
+    fma = "__ffma2_rn" if packed else "fmaf"
     monos = sorted({tuple(e) for terms in polys for _, e in terms if sum(e) > 0}, key=key)
     uses = {}
     for j, terms in enumerate(polys):
@@ -107,15 +114,17 @@ def _emit_streamed(lines, polys, outputs):
             if not started[j][k]:
                 started[j][k] = True
                 if k == 0 and consts[j] != 0.0:
-                    lines.append("    float2 %s = __ffma2_rn(%s, %s, %s);" % (acc, _c2(c), var, _c2(consts[j])))
-                else:
+                    lines.append("    %s %s = %s(%s, %s, %s);" % (ty, acc, fma, cst(c), var, cst(consts[j])))
+                elif packed:
                     lines.append("    float2 %s = __fmul2_rn(%s, %s);" % (acc, _c2(c), var))
+                else:
+                    lines.append("    float %s = %s * %s;" % (acc, _fmt(c), var))
             else:
-                lines.append("    %s = __ffma2_rn(%s, %s, %s);" % (acc, _c2(c), var, acc))
+                lines.append("    %s = %s(%s, %s, %s);" % (acc, fma, cst(c), var, acc))
             ffma += 1
 
     body = []
-    dag = Dag(body, "m", True)
+    dag = Dag(body, "m", packed)
     for i in range(5):
         t = [0] * 5
         t[i] = 1
@@ -131,11 +140,13 @@ def _emit_streamed(lines, polys, outputs):
     for j, out in enumerate(outputs):
         accs = ["%s_%d" % (names[j], k) for k in range(2) if started[j][k]]
         if not accs:
-            lines.append("    %s = %s;" % (out, _c2(consts[j])))
+            lines.append("    %s = %s;" % (out, cst(consts[j])))
         elif len(accs) == 1:
             lines.append("    %s = %s;" % (out, accs[0]))
-        else:
+        elif packed:
             lines.append("    %s = __fadd2_rn(%s, %s);" % (out, accs[0], accs[1]))
+        else:
+            lines.append("    %s = %s + %s;" % (out, accs[0], accs[1]))
     lines.append("  }")
     return lines, dag.muls, ffma
 
@@ -150,6 +161,8 @@ def emit_group(name, signature, polys, outputs, packed=False):
     lines = ["  LB_DEV void %s(%s) const {" % (name, signature), "    const %s b0 = b[0], b1 = b[1], b2 = b[2], b3 = b[3], b4 = b[4];" % ty]
     if packed and PACKED_ORDER != "grouped":
         return _emit_streamed(lines, polys, outputs)
+    if not packed and SCALAR_ORDER != "grouped":
+        return _emit_streamed(lines, polys, outputs, packed=False, order=SCALAR_ORDER)
     dag = Dag(lines, "m", packed)
     monos = sorted({tuple(e) for terms in polys for _, e in terms if sum(e) > 0}, key=lambda t: (sum(t), t))
     for m in monos:
@@ -257,10 +270,10 @@ def lens_unit(lens) -> tuple[str, dict]:
 # tuning knobs: resident blocks per SM the register allocator must allow ("" = compiler's choice).
 # Measured on B200 (lens 5, C2/C3): the scalar K1 was issue-bound and flat from 3 to 5 blocks (116 -> 96 registers); the
 # packed two-rays-per-thread K1 is FMA-pipe/latency-bound and wants warps: 4.94e9 rays/s at 3 blocks (156 registers),
-# 5.24e9 at 4 (128 registers, 8 bytes of spill).  K2 gains 6.7 % at 4 blocks (154 -> 128 registers, no spills) and loses
-# it again at 5 (96, spills).
+# 5.24e9 at 4 (128 registers, 8 bytes of spill).  K2 (latency-bound): 6.36e8 splats/s at 3 blocks, 6.70e8 at 4, and with
+# the lexicographic bodies 7.01e8 at 4, 7.43e8 at 5 (96 registers, no spill), 7.44e8 at 6 (80, spills).
 K1_MIN_BLOCKS = ", " + os.environ.get("LB_K1_MINBLOCKS", "4")
-K2_MIN_BLOCKS = ", " + os.environ.get("LB_K2_MINBLOCKS", "4")
+K2_MIN_BLOCKS = ", " + os.environ.get("LB_K2_MINBLOCKS", "5")
 
 
 def emit_cuda(out_dir: str, only=None):
