@@ -117,7 +117,6 @@ LB_DEV void camera_create_ray(const E &ev, const CamConsts<float> &cam, const Ra
 // the issue slots of the polynomial code while every half stays bit-identical to the scalar body.  A thread owns
 // rays j and j + ceil(n/2) (both halves' loads and stores stay fully coalesced) and walks their three traces in
 // lockstep; whatever is not polynomial runs once per half as before.
-LB_DEV float lo_hi(const float2 &v, int h) { return h ? v.y : v.x; }
 
 // pt_sample_aperture for two traces in lockstep; a half that has converged (or is off) is no longer updated
 template <typename E>

@@ -318,12 +318,10 @@ LB_DEV bool lt_continue(const LtState<T> &s) {  // for(k<100 && (sqr_err>eps || 
   const T eps = T(1e-8);
   return s.k < 100 && (s.sqr_err > eps || s.sqr_ap_err > eps) && s.error == 0;
 }
-template <typename T, typename E, typename C>
-LB_DEV void lt_iterate(const E &ev, const C &cam, const T scene[3], T ax, T ay, T lambda, LtState<T> &s) {
+// everything of one loop trip after the 14 polynomials (s.out already holds the outer-pupil point)
+template <typename T, typename C>
+LB_DEV void lt_iterate_tail(const C &cam, const T scene[3], T ax, T ay, const T ap[2], const T J[4], const T K[4], LtState<T> &s) {
   const T prev_sqr_err = s.sqr_err, prev_sqr_ap_err = s.sqr_ap_err;
-  const T b[5] = {s.x, s.y, s.dx, s.dy, lambda};
-  T ap[2], J[4], K[4];
-  ev.lt_all(b, ap, J, s.out, K);
   const T da0 = ax - ap[0], da1 = ay - ap[1];
   s.sqr_ap_err = da0 * da0 + da1 * da1;
   const T invdetap = T(1) / (J[0] * J[3] - J[1] * J[2]);
@@ -351,6 +349,38 @@ LB_DEV void lt_iterate(const E &ev, const C &cam, const T scene[3], T ax, T ay, 
   if (s.k < 10) error = 0;  // "error reset (k<10)", tests/aperture_sampling_debug/writout.txt:40
   s.error = error;
   s.k += 1;
+}
+template <typename T, typename E, typename C>
+LB_DEV void lt_iterate(const E &ev, const C &cam, const T scene[3], T ax, T ay, T lambda, LtState<T> &s) {
+  const T b[5] = {s.x, s.y, s.dx, s.dy, lambda};
+  T ap[2], J[4], K[4];
+  ev.lt_all(b, ap, J, s.out, K);
+  lt_iterate_tail(cam, scene, ax, ay, ap, J, K, s);
+}
+// One loop trip for TWO independent solves at once: the 14 polynomials go through the packed FP32 instructions
+// (Eval::lt_all2, FFMA2/FMUL2 of sm_100a: two solves per issued instruction), the rest runs per half.  A half that is
+// not `on` keeps its state untouched.
+LB_DEV float lo_hi(const float2 &v, int h) { return h ? v.y : v.x; }
+template <typename E, typename C>
+LB_DEV void lt_iterate2(const E &ev, const C &cam, const float scene[3], const float ax[2], const float ay[2], const float lambda[2],
+                        LtState<float> s[2], const bool on[2]) {
+  float2 b[5], ap[2], J[4], out[4], K[4];
+  b[0] = make_float2(s[0].x, s[1].x);
+  b[1] = make_float2(s[0].y, s[1].y);
+  b[2] = make_float2(s[0].dx, s[1].dx);
+  b[3] = make_float2(s[0].dy, s[1].dy);
+  b[4] = make_float2(lambda[0], lambda[1]);
+  ev.lt_all2(b, ap, J, out, K);
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    if (!on[h]) continue;
+    const float aph[2] = {lo_hi(ap[0], h), lo_hi(ap[1], h)};
+    const float Jh[4] = {lo_hi(J[0], h), lo_hi(J[1], h), lo_hi(J[2], h), lo_hi(J[3], h)};
+    const float Kh[4] = {lo_hi(K[0], h), lo_hi(K[1], h), lo_hi(K[2], h), lo_hi(K[3], h)};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s[h].out[k] = lo_hi(out[k], h);
+    lt_iterate_tail(cam, scene, ax[h], ay[h], aph, Jh, Kh, s[h]);
+  }
 }
 // after the loop: final pupil test and transmittance; returns max(0, out[4])
 template <typename T, typename E, typename C>
