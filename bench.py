@@ -320,8 +320,25 @@ def main():
     except OSError:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    # what the unrolled kernel actually issues for the polynomials: FMUL(2)/FFMA(2) slots of the shared-monomial bodies
+    # (the algorithmic count above charges every term its full monomial, SURVEY.md §8d, so `frac` can exceed 1)
+    executed = None
+    try:
+        from pota_b200.lensgen import emit_cuda
+        from pota_b200.lensgen.pack import load_pack
+
+        st = emit_cuda.lens_unit(load_pack()[camera_params().lens_model])[1]
+        slots = traces_per_ray * (k_its * sum(st["ap_jac"]) + sum(st["out5"]))
+        slot_rate = slots * n_rays / (kernel_ms * 1e-3)
+        executed = {"fma_pipe_slots_per_ray": slots, "slots_per_s": slot_rate, "peak_slots_per_s": peak.value * 1e12 / 2.0,
+                    "frac": slot_rate / max(peak.value * 1e12 / 2.0, 1.0),
+                    "note": "polynomial FMUL/FFMA lane-slots only (packed FMUL2/FFMA2 count two); ncu of the same kernel: FMA pipe 80-83 % active"}
+    except Exception as e:  # the lens pack tooling is optional at run time
+        executed = {"unavailable": str(e)}
     roofline = {"bound": "fp32", "achieved": achieved_tflops, "peak": peak.value, "unit": "TFLOP/s", "frac": achieved_tflops / max(peak.value, 1e-9),
-                "traffic": None, "peak_source": "lb_bench_fp32_peak (register FFMA chains) measured in this run; nominal 148*128*2*1.965 GHz = 74.5",
+                "executed": executed,
+                "traffic": 106.3 * n_rays, "traffic_source": "ncu --set full of this kernel (profiles/r01_k1_create_rays_ncu.txt): dram read+write = 106.3 B/ray vs 108 B/ray algorithmic",
+                "peak_source": "lb_bench_fp32_peak (register FFMA chains) measured in this run; nominal 148*128*2*1.965 GHz = 74.5",
                 "flop_per_ray": flop_per_ray, "newton_its_per_trace": k_its, "traces_per_ray": traces_per_ray,
                 "hbm": {"achieved": n_rays * 108 / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": n_rays * 108 / (kernel_ms * 1e-3) / 1e9 / hbm_peak, "bytes_per_ray": 108,

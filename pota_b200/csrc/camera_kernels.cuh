@@ -147,38 +147,47 @@ LB_DEV void pt_sample_aperture2(const E &ev, const float x[2], const float y[2],
   }
 }
 
-struct FwRay2 {
-  float o[3][2], d[3][2];
-  bool ok[2];
-};
-
-// Camera::trace_ray_fw_po (lentil.h:283-427) for two rays in lockstep.  `u` carries the aperture sample of each half:
-// the main trace writes it, the derivative traces reuse it (they are called with the same r1, r2: lentil_camera.cpp:111-112).
-// A derivative trace that fails would repeat identical work vignetting_retries times (lentil.h:296,313): one pass suffices.
+// Camera::trace_ray_fw_po (lentil.h:283-427) for two rays in lockstep, up to the outer-pupil point `out` of each half.
+// `ux, uy` carry the aperture sample of each half: the main trace writes it, the derivative traces reuse it (they are
+// called with the same r1, r2: lentil_camera.cpp:111-112).  A derivative trace that fails would repeat identical work
+// vignetting_retries times (lentil.h:296,313): one pass suffices.  Code that is not polynomial and not needed in
+// lockstep runs per half in ROLLED loops (pick/put): one copy in the instruction cache.
 template <typename E>
-LB_DEV void trace_pair_fw_po(const E &ev, const CamConsts<float> &cam, const float sx[2], const float sy[2], float r1[2], float r2[2],
-                             float ux[2], float uy[2], bool deriv_ray, const uint32_t ray_id[2], const bool valid[2], FwRay2 &r,
-                             int tries[2]) {
+LB_DEV void trace_pair_fw_po(const E &ev, const CamConsts<float> &cam, const float sx[2], const float sy[2], float (&r1)[2], float (&r2)[2],
+                             float (&ux)[2], float (&uy)[2], bool deriv_ray, const uint32_t (&ray_id)[2], const bool valid[2],
+                             float (&out)[4][2], bool (&success)[2], int (&tries)[2]) {
   bool active[2] = {valid[0], valid[1]};
-  bool success[2] = {false, false};
-  float out[4][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+  success[0] = success[1] = false;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) out[k][0] = out[k][1] = 0.f;
   tries[0] = tries[1] = 0;
   while (active[0] || active[1]) {
+    if (cam.enable_dof && !deriv_ray) {
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        if (!pick(active, h)) continue;
+        float a = pick(r1, h), b = pick(r2, h);
+        const int tr = pick(tries, h);
+        if (tr > 0) {  // retry lens sample: counter RNG instead of the global xor128 (lentil.h:313-316)
+          uint32_t seed = tea8(pick(ray_id, h), (uint32_t)tr);
+          a = lcg_rng(seed);
+          b = lcg_rng(seed);
+          put(r1, h, a);
+          put(r2, h, b);
+        }
+        float u, v;
+        if (cam.bokeh_n > 0) bokeh_sample(cam, a, b, u, v);
+        else if (cam.blades < 2) concentric_disk_sample(a, b, u, v);
+        else sample_triangular_aperture(u, v, a, b, 1.0f, cam.blades);
+        put(ux, h, u);
+        put(uy, h, v);
+      }
+    }
     float x[2], y[2], dx[2] = {0.f, 0.f}, dy[2] = {0.f, 0.f}, ax[2], ay[2];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       x[h] = sx[h] * cam.sensor_half;
       y[h] = sy[h] * cam.sensor_half;
-      if (active[h] && cam.enable_dof && !deriv_ray) {
-        if (tries[h] > 0) {  // retry lens sample: counter RNG instead of the global xor128 (lentil.h:313-316)
-          uint32_t seed = tea8(ray_id[h], (uint32_t)tries[h]);
-          r1[h] = lcg_rng(seed);
-          r2[h] = lcg_rng(seed);
-        }
-        if (cam.bokeh_n > 0) bokeh_sample(cam, r1[h], r2[h], ux[h], uy[h]);
-        else if (cam.blades < 2) concentric_disk_sample(r1[h], r2[h], ux[h], uy[h]);
-        else sample_triangular_aperture(ux[h], uy[h], r1[h], r2[h], 1.0f, cam.blades);
-      }
       ax[h] = ux[h] * cam.aperture_radius;
       ay[h] = uy[h] * cam.aperture_radius;
     }
@@ -208,24 +217,22 @@ LB_DEV void trace_pair_fw_po(const E &ev, const CamConsts<float> &cam, const flo
       else { ++tries[h]; if (deriv_ray || tries[h] > cam.vignetting_retries) active[h] = false; }
     }
   }
+}
+
+// outer-pupil point -> camera-space ray in scene units, normalised (lentil.h:387-425)
+LB_DEV void finish_fw_ray(const CamConsts<float> &cam, const float out[4], bool success, float o[3], float d[3], bool &ok) {
+  float pos[3], dir[3];
+  outer_to_cs(cam, out, pos, dir);
+  // origin/direction *= -{1,.1,.01,.001} (lentil.h:395-416), then AiV3Normalize
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const float o4[4] = {out[0][h], out[1][h], out[2][h], out[3][h]};
-    float pos[3], dir[3];
-    outer_to_cs(cam, o4, pos, dir);
-    float o[3];
+  for (int k = 0; k < 3; ++k) { o[k] = pos[k] * cam.unit_scale; dir[k] *= cam.unit_scale; }
+  const float len = sqrtf(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
+  const float inv = len != 0.f ? 1.0f / len : 0.f;
+  ok = success;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) { o[k] = pos[k] * cam.unit_scale; dir[k] *= cam.unit_scale; }
-    const float len = sqrtf(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
-    const float inv = len != 0.f ? 1.0f / len : 0.f;
-    bool ok = success[h];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      r.o[k][h] = o[k];
-      r.d[k][h] = dir[k] * inv;
-      if (r.o[k][h] != r.o[k][h] || r.d[k][h] != r.d[k][h]) ok = false;  // NaN bailout (lentil.h:421-425)
-    }
-    r.ok[h] = ok;
+  for (int k = 0; k < 3; ++k) {
+    d[k] = dir[k] * inv;
+    if (o[k] != o[k] || d[k] != d[k]) ok = false;  // NaN bailout (lentil.h:421-425)
   }
 }
 
@@ -259,27 +266,34 @@ LB_DEV void camera_create_ray_pair(const E &ev, const CamConsts<float> &cam, con
       tsx[h] = t == 1 ? sx[h] + (dsx[h] * fd) : sx[h];
       tsy[h] = t == 2 ? sy[h] + (dsy[h] * fd) : sy[h];
     }
-    FwRay2 r;
+    float out[4][2];
+    bool success[2];
     int tr[2];
-    trace_pair_fw_po(ev, cam, tsx, tsy, r1, r2, ux, uy, t != 0, ray_id, valid, r, tr);
+    trace_pair_fw_po(ev, cam, tsx, tsy, r1, r2, ux, uy, t != 0, ray_id, valid, out, success, tr);
     float *po = t == 0 ? io.origin : (t == 1 ? io.dOdx : io.dOdy);
     float *pd = t == 0 ? io.dir : (t == 1 ? io.dDdx : io.dDdy);
-#pragma unroll
+#pragma unroll 1
     for (int h = 0; h < 2; ++h) {
-      if (!valid[h]) continue;
+      if (!pick(valid, h)) continue;
+      const float o4[4] = {pick(out[0], h), pick(out[1], h), pick(out[2], h), pick(out[3], h)};
+      float o[3], d[3];
+      bool ok;
+      finish_fw_ray(cam, o4, pick(success, h), o, d, ok);
+      const size_t ih = pick(i, h);
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
         if (t == 0) {
-          mo[k][h] = r.o[k][h]; md[k][h] = r.d[k][h];
-          if (po) po[k * P + i[h]] = r.o[k][h];
-          if (pd) pd[k * P + i[h]] = r.d[k][h];
-          if (io.weight) io.weight[k * P + i[h]] = r.ok[h] ? cam.exposure : 0.f * cam.exposure;
+          put(mo[k], h, o[k]);
+          put(md[k], h, d[k]);
+          if (po) po[k * P + ih] = o[k];
+          if (pd) pd[k * P + ih] = d[k];
+          if (io.weight) io.weight[k * P + ih] = ok ? cam.exposure : 0.f * cam.exposure;
         } else {
-          if (po) po[k * P + i[h]] = (r.o[k][h] - mo[k][h]) * inv_fd;
-          if (pd) pd[k * P + i[h]] = (r.d[k][h] - md[k][h]) * inv_fd;
+          if (po) po[k * P + ih] = (o[k] - pick(mo[k], h)) * inv_fd;
+          if (pd) pd[k * P + ih] = (d[k] - pick(md[k], h)) * inv_fd;
         }
       }
-      if (t == 0 && io.tries) io.tries[i[h]] = tr[h];
+      if (t == 0 && io.tries) io.tries[ih] = pick(tr, h);
     }
   }
 }

@@ -357,31 +357,14 @@ LB_DEV void lt_iterate(const E &ev, const C &cam, const T scene[3], T ax, T ay, 
   ev.lt_all(b, ap, J, s.out, K);
   lt_iterate_tail(cam, scene, ax, ay, ap, J, K, s);
 }
-// One loop trip for TWO independent solves at once: the 14 polynomials go through the packed FP32 instructions
-// (Eval::lt_all2, FFMA2/FMUL2 of sm_100a: two solves per issued instruction), the rest runs per half.  A half that is
-// not `on` keeps its state untouched.
+// half of a packed pair (two-rays-per-thread forward kernel, camera_kernels.cuh)
 LB_DEV float lo_hi(const float2 &v, int h) { return h ? v.y : v.x; }
-template <typename E, typename C>
-LB_DEV void lt_iterate2(const E &ev, const C &cam, const float scene[3], const float ax[2], const float ay[2], const float lambda[2],
-                        LtState<float> s[2], const bool on[2]) {
-  float2 b[5], ap[2], J[4], out[4], K[4];
-  b[0] = make_float2(s[0].x, s[1].x);
-  b[1] = make_float2(s[0].y, s[1].y);
-  b[2] = make_float2(s[0].dx, s[1].dx);
-  b[3] = make_float2(s[0].dy, s[1].dy);
-  b[4] = make_float2(lambda[0], lambda[1]);
-  ev.lt_all2(b, ap, J, out, K);
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    if (!on[h]) continue;
-    const float aph[2] = {lo_hi(ap[0], h), lo_hi(ap[1], h)};
-    const float Jh[4] = {lo_hi(J[0], h), lo_hi(J[1], h), lo_hi(J[2], h), lo_hi(J[3], h)};
-    const float Kh[4] = {lo_hi(K[0], h), lo_hi(K[1], h), lo_hi(K[2], h), lo_hi(K[3], h)};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) s[h].out[k] = lo_hi(out[k], h);
-    lt_iterate_tail(cam, scene, ax[h], ay[h], aph, Jh, Kh, s[h]);
-  }
-}
+// element h of a register-resident pair, for loops over a warp-uniform half index that must stay rolled (one copy of
+// the loop body in the instruction cache): selects instead of indexed addressing
+template <typename T>
+LB_DEV T pick(const T (&a)[2], int h) { return h ? a[1] : a[0]; }
+template <typename T>
+LB_DEV void put(T (&a)[2], int h, T v) { if (h) a[1] = v; else a[0] = v; }
 // after the loop: final pupil test and transmittance; returns max(0, out[4])
 template <typename T, typename E, typename C>
 LB_DEV T lt_finish(const E &ev, const C &cam, T lambda, const LtState<T> &s) {

@@ -245,11 +245,6 @@ def lens_unit(lens) -> tuple[str, dict]:
                                  ["ap[0]", "ap[1]", "J[0]", "J[1]", "J[2]", "J[3]", "out[0]", "out[1]", "out[2]", "out[3]", "K[0]", "K[1]", "K[2]", "K[3]"])
     src += body
     stats["lt_all"] = (mul, ffma)
-    body, _, _ = emit_group("lt_all2", "const float2 b[5], float2 ap[2], float2 J[4], float2 out[4], float2 K[4]",
-                            [P["ap_x"], P["ap_y"]] + dap + [P["out_x"], P["out_y"], P["out_dx"], P["out_dy"]] + dout,
-                            ["ap[0]", "ap[1]", "J[0]", "J[1]", "J[2]", "J[3]", "out[0]", "out[1]", "out[2]", "out[3]", "K[0]", "K[1]", "K[2]", "K[3]"],
-                            packed=True)
-    src += body
     src += ["};", "",
             "__global__ void __launch_bounds__(128%s)" % K1_MIN_BLOCKS,
             "k_create_rays_%d(const __grid_constant__ CamConsts<float> cam, const __grid_constant__ RayIO io, size_t n, uint64_t ray_id_base) {" % k,
@@ -260,7 +255,7 @@ def lens_unit(lens) -> tuple[str, dict]:
             "__global__ void __launch_bounds__(128%s)" % K2_MIN_BLOCKS,
             "k_filter_splat_%d(const __grid_constant__ CamConsts<float> cam, const __grid_constant__ FilterConsts fc, const __grid_constant__ AovSet aovs," % k,
             "                  const __grid_constant__ SampleIO s, const WorkItem *__restrict__ work, FilterCounters *__restrict__ counters, uint64_t sample_base) {",
-            "  splat_persistent<%s>(Eval%d{}, cam, fc, aovs, s, work, counters, sample_base);" % (K2_PACKED, k),
+            "  splat_persistent(Eval%d{}, cam, fc, aovs, s, work, counters, sample_base);" % k,
             "}", "", "}  // namespace", "",
             "cudaError_t launch_fw_lens_%d(const CamConsts<float> &cam, const RayIO &io, size_t n, uint64_t ray_id_base, cudaStream_t stream) {" % k,
             "  k_create_rays_%d<<<(unsigned)(((n + 1) / 2 + 127) / 128), 128, 0, stream>>>(cam, io, n, ray_id_base);" % k,
@@ -279,7 +274,6 @@ def lens_unit(lens) -> tuple[str, dict]:
 # the lexicographic bodies 7.01e8 at 4, 7.43e8 at 5 (96 registers, no spill), 7.44e8 at 6 (80, spills).
 K1_MIN_BLOCKS = ", " + os.environ.get("LB_K1_MINBLOCKS", "4")
 K2_MIN_BLOCKS = ", " + os.environ.get("LB_K2_MINBLOCKS", "5")
-K2_PACKED = "true" if os.environ.get("LB_K2_PACKED", "1") != "0" else "false"  # two attempt slots per lane, FFMA2 bodies
 
 
 def emit_cuda(out_dir: str, only=None):
