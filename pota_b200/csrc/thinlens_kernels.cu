@@ -108,8 +108,10 @@ LB_DEV V3f coma_perturb(V3f dir_from_lens, V3f ray, float abb_coma, bool reverse
 }
 
 // ---- forward: Camera::trace_ray_fw_thinlens, lentil.h:431-569 ------------------------------------------------
+// (ux, uy): the unit-disk lens sample.  The main trace computes it; the derivative traces are called with the same
+// r1, r2 (lentil_camera.cpp:111-112) and reuse it instead of sampling again.
 LB_DEV FwRay trace_ray_fw_thinlens(const CamConsts<float> &cam, const ThinConsts &tl, float sx, float sy, float &r1, float &r2,
-                                   bool deriv_ray, uint32_t ray_id, int &tries) {
+                                   double &ux, double &uy, bool deriv_ray, uint32_t ray_id, int &tries) {
   tries = 0;
   bool ray_succes = false;
   FwRay r;
@@ -123,21 +125,21 @@ LB_DEV FwRay trace_ray_fw_thinlens(const CamConsts<float> &cam, const ThinConsts
     }
     const V3f p{(float)((double)s0 * tl.sensor_half), (float)((double)s1 * tl.sensor_half), -tl.focal_length};
     const V3f dir_from_center = normalize3f(p);
-    double ux = 0.0, uy = 0.0;
-    if (cam.enable_dof) {
-      if (!deriv_ray && tries > 0) {  // counter RNG instead of the global xor128 (lentil.h:460-463), as in the PO path
+    if (cam.enable_dof && !deriv_ray) {
+      if (tries > 0) {  // counter RNG instead of the global xor128 (lentil.h:460-463), as in the PO path
         uint32_t seed = tea8(ray_id, (uint32_t)tries);
         r1 = lcg_rng(seed);
         r2 = lcg_rng(seed);
       }
       thin_unit_disk(cam, tl, r1, r2, ux, uy);
+      ux *= (double)tl.bokeh_anamorphic;
     }
-    ux *= (double)tl.bokeh_anamorphic;
     const V3f lens{(float)(ux * tl.aperture_radius), (float)(uy * tl.aperture_radius), 0.0f};
     const float intersection = (float)fabs(tl.focus_distance / (double)lerpf(0.0f, dir_from_center.z, 1.0f));
     const V3f focusPoint{dir_from_center.x * intersection, dir_from_center.y * intersection, dir_from_center.z * intersection};
     V3f dir_from_lens = normalize3f(V3f{focusPoint.x - lens.x, focusPoint.y - lens.y, focusPoint.z - lens.z});
-    const float abb_coma_multiplied = tl.abb_coma * coma_multiplier(tl, dir_from_center, ux, uy);
+    // abb_coma == 0 (the default): 0 * (finite multiplier) is +-0 and the perturbation below is the identity
+    const float abb_coma_multiplied = tl.abb_coma == 0.0f ? 0.0f : tl.abb_coma * coma_multiplier(tl, dir_from_center, ux, uy);
     dir_from_lens = coma_perturb(dir_from_lens, dir_from_lens, abb_coma_multiplied, false);
     if (tl.optical_vignetting_distance > 0.0f && !deriv_ray) {
       if (!optical_vignetting_square(lens, dir_from_lens, (float)tl.aperture_radius, tl)) { ++tries; continue; }
@@ -164,9 +166,10 @@ k_create_rays_thinlens(const __grid_constant__ CamConsts<float> cam, const __gri
   // the thin-lens trace is exact float arithmetic on both sides: the reference's own step is kept (no baseline stretch)
   const float step = 0.001f;
   int tries, td;
-  const FwRay m = trace_ray_fw_thinlens(cam, tl, sx, sy, r1, r2, false, ray_id, tries);
-  const FwRay ax = trace_ray_fw_thinlens(cam, tl, sx + (dsx * step), sy, r1, r2, true, ray_id, td);
-  const FwRay ay = trace_ray_fw_thinlens(cam, tl, sx, sy + (dsy * step), r1, r2, true, ray_id, td);
+  double ux = 0.0, uy = 0.0;
+  const FwRay m = trace_ray_fw_thinlens(cam, tl, sx, sy, r1, r2, ux, uy, false, ray_id, tries);
+  const FwRay ax = trace_ray_fw_thinlens(cam, tl, sx + (dsx * step), sy, r1, r2, ux, uy, true, ray_id, td);
+  const FwRay ay = trace_ray_fw_thinlens(cam, tl, sx, sy + (dsy * step), r1, r2, ux, uy, true, ray_id, td);
   const float w = m.ok ? cam.exposure : 0.f * cam.exposure;
   const size_t P = io.plane;
   const float inv_step = 1.0f / step;
@@ -208,7 +211,7 @@ LB_DEV int thinlens_attempt(const CamConsts<float> &cam, const ThinConsts &tl, c
   const V3f lens{(float)(ux * tl.aperture_radius), (float)(uy * tl.aperture_radius), 0.0f};
   V3f dir_from_center = normalize3f(P);
   V3f dir_lens_to_P = normalize3f(V3f{P.x - lens.x, P.y - lens.y, P.z - lens.z});
-  const float abb_coma_multiplied = tl.abb_coma * coma_multiplier(tl, dir_from_center, ux, uy);
+  const float abb_coma_multiplied = tl.abb_coma == 0.0f ? 0.0f : tl.abb_coma * coma_multiplier(tl, dir_from_center, ux, uy);
   dir_lens_to_P = coma_perturb(dir_lens_to_P, dir_from_center, abb_coma_multiplied, true);
   const float lenP = sqrtf(dot3f(P, P));
   const V3f Pp{lenP * dir_lens_to_P.x, lenP * dir_lens_to_P.y, lenP * dir_lens_to_P.z};
