@@ -1,10 +1,5 @@
 #!/bin/bash
 cd /root/repo
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_thinlens_gpu.py tests/test_crypto_gpu.py -q -m gpu --tb=short 2>&1 | tail -8 > gpurun_out/tl.log
-timeout 600 python bench.py --skip-e2e --skip-cpu --skip-splat --skip-crypto --steps 5 --warmup 3 2>&1 | tail -1 | python -c "
-import sys, json
-d = json.loads(sys.stdin.read())
-print('thin rays/s %.4g (hbm frac %.3f)  thin splats/s %.4g' % (d['thinlens']['rays']['value'], d['thinlens']['rays']['roofline']['frac'], d['thinlens']['splat']['value']))
-" >> gpurun_out/tl.log 2>&1
-cat gpurun_out/tl.log
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/multi_gpu_check.py > gpurun_out/mgpu.log 2>&1; tail -2 gpurun_out/mgpu.log
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 3 --warmup 3 > gpurun_out/bench_2gpu.json 2> gpurun_out/bench_2gpu.err; tail -2 gpurun_out/bench_2gpu.err; tail -1 gpurun_out/bench_2gpu.json | cut -c1-300
