@@ -35,6 +35,32 @@ CRYPTO_CASES = {
     "crypto_thinlens50_f1.4": dict(camera_type=abi.LB_CAMERA_THINLENS, focal_length_lentil=50.0, fstop=1.4, focus_dist=35.0, bidir_sample_mult=6),
 }
 CRYPTO_DEPTH, CRYPTO_SLOTS = 4, 16
+# the reference's own fixture of real source samples (input only): /root/reference/tests/cuda/sampledata.txt, rows
+# "r g b a depth x_cs y_cs z_cs" written by its CUDA prototype run of tests/cuda/lightgrid.ass (SURVEY.md §8c fixture 1)
+SAMPLEDATA = "/root/reference/tests/cuda/sampledata.txt"
+SAMPLEDATA_ROWS = 9 * 128
+SAMPLEDATA_CASES = {
+    "sampledata_thinlens50_f1.4": dict(camera_type=abi.LB_CAMERA_THINLENS, focal_length_lentil=50.0, fstop=1.4, focus_dist=35.0, bidir_sample_mult=4),
+    "sampledata_takumar50_f1.4": dict(camera_type=abi.LB_CAMERA_POLYNOMIAL_OPTICS, lens_model=5, fstop=1.4, focus_dist=35.0, bidir_sample_mult=2),
+}
+
+
+def sampledata_frame(rows, tan_fov, W, H, spp):
+    """Source samples from sampledata rows: runs of `spp` consecutive rows share the pixel the run's first row
+    projects to through a pinhole (filter_pixel needs AA^2 samples per call, lentil_filter.cpp:79-87)."""
+    n = rows.shape[0] // spp * spp
+    rows = rows[:n]
+    rgba = rows[:, 0:4].astype(np.float32)
+    pos = np.concatenate([rows[:, 5:8], rows[:, 4:5]], axis=1).astype(np.float32)  # xyz camera space, w = depth
+    first = pos[::spp]
+    sx = first[:, 0] / (-first[:, 2] * tan_fov)
+    sy = first[:, 1] / (-first[:, 2] * tan_fov)
+    px = np.clip(np.floor((sx + 1.0) * 0.5 * W), 0, W - 1).astype(np.int32)
+    py = np.clip(np.floor((1.0 - sy * (W / H)) * 0.5 * H), 0, H - 1).astype(np.int32)
+    for g in range(1, px.shape[0]):  # consecutive runs must differ in pixel, or the iterator would hand them over as one
+        if px[g] == px[g - 1] and py[g] == py[g - 1]:
+            px[g] = (px[g] + 1) % W
+    return np.repeat(px, spp), np.repeat(py, spp), rgba, pos
 
 
 def params(**kw):
@@ -95,6 +121,19 @@ def main():
             d[f"resolved{a}"] = r.resolve(a, fill=-7.0)
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **d)
         print(name, "largest id table", mx)
+    rows = np.loadtxt(SAMPLEDATA, max_rows=SAMPLEDATA_ROWS)
+    for name, kw in SAMPLEDATA_CASES.items():
+        p = abi.CameraParams.defaults(**kw)
+        r = ref.RefCamera(p)
+        W, H, spp = 480, 270, 9
+        px, py, rgba, pos = sampledata_frame(rows, r.state.tan_fov, W, H, spp)
+        aovs = [("RGBA", 0, 1)]
+        r.filter_begin(W, H, aovs, spp=spp)
+        r.filter_accumulate(px, py, rgba, pos, 1.0 / spp)
+        buf, wgt = r.buffers(0)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), params=np.frombuffer(bytes(p), np.uint8), W=W, H=H, spp=spp,
+                            px=px, py=py, rgba=rgba, pos_cs=pos, buffer0=buf, weight=wgt, resolved0=r.resolve(0))
+        print(name, "rows", rgba.shape[0], "energy", float(buf[..., :3].sum()), "weight", float(wgt.sum()))
 
 
 if __name__ == "__main__":

@@ -18,6 +18,7 @@ IN_KEYS = ("sx", "sy", "dsx", "dsy", "lensx", "lensy")
 RAY_FILES = sorted(glob.glob(os.path.join(GOLD, "rays_*.npz")))
 FILTER_FILES = sorted(glob.glob(os.path.join(GOLD, "filter_*.npz")))
 CRYPTO_FILES = sorted(glob.glob(os.path.join(GOLD, "crypto_*.npz")))
+SAMPLEDATA_FILES = sorted(glob.glob(os.path.join(GOLD, "sampledata_*.npz")))
 
 
 def _params(g):
@@ -37,7 +38,7 @@ def _frame(g, tan_fov):
 
 
 def test_fixtures_present():
-    assert len(RAY_FILES) >= 3 and len(FILTER_FILES) >= 2 and len(CRYPTO_FILES) >= 2
+    assert len(RAY_FILES) >= 3 and len(FILTER_FILES) >= 2 and len(CRYPTO_FILES) >= 2 and len(SAMPLEDATA_FILES) >= 2
 
 
 @pytest.mark.parametrize("path", RAY_FILES, ids=os.path.basename)
@@ -68,6 +69,51 @@ def test_oracle_reproduces_reference_framebuffers(path):
         np.testing.assert_array_equal(buf, g[f"buffer{a}"])
         np.testing.assert_array_equal(wgt, g["weight"])
         np.testing.assert_array_equal(cam.resolve(a), g[f"resolved{a}"])
+
+
+@pytest.mark.parametrize("path", SAMPLEDATA_FILES, ids=os.path.basename)
+def test_oracle_reproduces_reference_on_sampledata_rows(path):
+    """Source samples = literal rows of the reference's tests/cuda/sampledata.txt (its CUDA prototype's input, the one
+    fixture of real renderer samples it ships); framebuffers = the compiled reference's output for them."""
+    g = np.load(path)
+    cam = orc.OracleCamera(_params(g))
+    W, H, spp = int(g["W"]), int(g["H"]), int(g["spp"])
+    cam.filter_begin(W, H, [("RGBA", 0, 1)])
+    cam.filter_accumulate(g["px"], g["py"], g["rgba"], g["pos_cs"], 1.0 / spp)
+    st = cam.filter_stats()
+    assert st["redistributed"] == g["px"].shape[0] and st["splats"] > 20 * st["redistributed"]  # every row is a highlight out of focus
+    buf, wgt = cam.buffers(0)
+    np.testing.assert_array_equal(buf, g["buffer0"])
+    np.testing.assert_array_equal(wgt, g["weight"])
+    np.testing.assert_array_equal(cam.resolve(0), g["resolved0"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", SAMPLEDATA_FILES, ids=os.path.basename)
+def test_gpu_against_reference_on_sampledata_rows(path, kernel_kind):
+    import torch
+
+    from pota_b200.camera import Camera
+
+    g = np.load(path)
+    p = _params(g)
+    cam = Camera(p, None, device=0)
+    W, H, spp = int(g["W"]), int(g["H"]), int(g["spp"])
+    cam.filter_begin(W, H, [("RGBA", 0, 1)])
+    cam.filter_accumulate(*[torch.from_numpy(g[k]).cuda() for k in ("px", "py", "rgba", "pos_cs")], 1.0 / spp)
+    torch.cuda.synchronize()
+    st = cam.filter_stats()
+    assert st["redistributed"] == g["px"].shape[0]
+    buf, wgt = cam.buffers(0)
+    exact = p.camera_type == abi.LB_CAMERA_THINLENS
+    l1 = np.abs(buf - g["buffer0"]).sum() / np.abs(g["buffer0"]).sum()
+    assert l1 <= (1e-3 if exact else 5e-3), l1
+    np.testing.assert_allclose(buf.sum(dtype=np.float64), g["buffer0"].sum(dtype=np.float64), rtol=2e-3)
+    np.testing.assert_allclose(wgt.sum(dtype=np.float64), g["weight"].sum(dtype=np.float64), rtol=2e-3)
+    res = cam.resolve(0).cpu().numpy()
+    peak = float(np.abs(g["resolved0"]).max())
+    mse = float(((res.astype(np.float64) - g["resolved0"].astype(np.float64)) ** 2).mean())
+    assert mse == 0 or 10.0 * np.log10(peak * peak / mse) >= 50.0
 
 
 def _crypto_inputs(g, tan_fov):

@@ -8,6 +8,7 @@ say where a tolerance is used instead.  Skipped when libref.so has not been buil
 /root/reference; `make -C oracle -f ref.mk`).
 """
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -340,3 +341,30 @@ def test_cryptomatte_accumulate_and_ranked_resolve(kw):
     res4 = o.resolve(3, fill=-7.0)  # rank 4: most rows end early
     done = res4[..., 1] != -7.0
     assert done.any() and (~done).any()
+
+
+def test_reverse_trace_on_reference_debug_positions(libs):
+    """The reference's own fixture of camera-space sample positions (tests/po_bidir_debug/
+    po_bidir_spheres_debug_position.txt, 3699 rows, input only): trace_ray_bw_po + get_coc_thinlens on every row,
+    reference vs oracle, bit for bit."""
+    path = "/root/reference/tests/po_bidir_debug/po_bidir_spheres_debug_position.txt"
+    if not os.path.exists(path):
+        pytest.skip("reference checkout not present")
+    import re
+    rows = np.array([[float(v) for v in re.findall(r"[-+0-9.eE]+", ln)] for ln in open(path) if ln.strip()], dtype=np.float64)
+    assert rows.shape == (3699, 3)
+    O, R = libs
+    p = po_params(fstop=2.0, focus_dist=100.0)
+    o, r = orc.OracleCamera(p), ref.RefCamera(p)
+    s1, s2 = (C.c_double * 2)(), (C.c_double * 2)()
+    hits = 0
+    for i, P in enumerate(rows):
+        # the filter hands trace_ray_bw_po the target -P_cs * 10 (lentil_filter.cpp:271)
+        tgt = (C.c_double * 3)(*(-P * 10.0))
+        px, py, tot = (i * 7) % 1920, (i * 13) % 1080, i % 50
+        ok1 = O.orc_trace_ray_bw_po(o._h, tgt, px, py, tot, C.c_float(0.55), s1)
+        ok2 = R.ref_trace_ray_bw_po(r._h, tgt, px, py, tot, C.c_float(0.55), s2)
+        assert ok1 == ok2 and (not ok1 or list(s1) == list(s2)), i
+        hits += int(bool(ok1))
+        assert O.orc_get_coc_thinlens(o._h, float(np.float32(P[2]))) == R.ref_get_coc_thinlens(r._h, float(np.float32(P[2])))
+    assert hits > 3000
