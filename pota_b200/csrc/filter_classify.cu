@@ -68,11 +68,13 @@ k_filter_classify(const __grid_constant__ FilterConsts fc, const __grid_constant
   int samples = 0;
   float add_energy = 0.f;
   float csp[3] = {0.f, 0.f, 0.f};
+  float depth = 0.f, debug_val = 0.f;
+  unsigned pixel = 0u;
   if (active) {
     float4 sample = __ldg(s.rgba + i);
     const float4 pz = __ldg(s.pos_cs + i);
     csp[0] = pz.x; csp[1] = pz.y; csp[2] = pz.z;
-    const float depth = pz.w;
+    depth = pz.w;
     // lentil_filter.cpp:119-133
     const bool small = fabsf(csp[0]) < 1.0e-4f && fabsf(csp[1]) < 1.0e-4f && fabsf(csp[2]) < 1.0e-4f;
     if ((depth == 1.0e30f || small) && fc.enable_skydome) {
@@ -103,28 +105,66 @@ k_filter_classify(const __grid_constant__ FilterConsts fc, const __grid_constant
     if (sf < 4.f) sf = 4.f;
     if (sf > 2000.f) sf = 2000.f;
     samples = (int)sf;
-    const float debug_val = (float)(samples * (redistribute ? 1 : 0));  // lentil_debug value, taken at :209-211
+    debug_val = (float)(samples * (redistribute ? 1 : 0));  // lentil_debug value, taken at :209-211
     if (fc.camera_type == 1 && (double)fabsf(csp[2]) < fc.lens_length_tenth) redistribute = false;  // :240, PolynomialOptics case only
     const int px = __ldg(s.px + i), py = __ldg(s.py + i);
     for (int a = 0; a < fc.n_aov; ++a)  // lentil_filter.cpp:167-169
       if (aovs.filter[a] == 2) crypto_build_cache(aovs, s, a, i);
-    if (!redistribute) {
-      // filter_and_add_to_buffer_new (lentil.h:938-955): every AOV, own pixel, weight inv_density
-      const unsigned pixel = (unsigned)fc.xres * (unsigned)py + (unsigned)px;
-      const float white[3] = {1.f, 1.f, 1.f};
-      for (int a = 0; a < fc.n_aov; ++a) {
-        if (aovs.filter[a] == 2) { crypto_add(aovs, a, i, true, pixel, s.inv_density, counters); continue; }
-        const float4 v = aov_value(aovs, s, a, i, debug_val);
-        add_to_buffer(aovs, a, pixel, v, 0.0f, depth, s.inv_density, white, sample_base + i);
+    pixel = (unsigned)fc.xres * (unsigned)py + (unsigned)px;
+    if (aovs.debug_samples) aovs.debug_samples[i] = (uint16_t)debug_val;
+  }
+  const int lane = threadIdx.x & 31;
+  // filter_and_add_to_buffer_new (lentil.h:938-955) for the samples that are not redistributed: every AOV, own pixel,
+  // weight inv_density.  The renderer hands over a pixel's samples together, so consecutive lanes mostly share the
+  // pixel: gaussian AOVs are summed over each run of equal pixels inside the warp first (segmented shuffle
+  // reduction) and added with ONE reduction per run -- 16 same-address reductions per pixel at 16 spp otherwise
+  // serialise in L2.  Float sums are order-free here as in the reference (its threads race, lentil.h:828-829).
+  const bool pass = active && !redistribute;
+  if (__any_sync(0xffffffffu, pass)) {
+    const unsigned key = pass ? pixel : 0xFFFFFFFFu;
+    const unsigned prev = __shfl_up_sync(0xffffffffu, key, 1);
+    const bool head = lane == 0 || prev != key;
+    const unsigned heads = __ballot_sync(0xffffffffu, head);
+    const unsigned above = lane < 31 ? heads >> (lane + 1) : 0u;  // head flags of the lanes after this one
+    for (int a = 0; a < fc.n_aov; ++a) {
+      if (aovs.filter[a] == 2) {  // cryptomatte tables: per sample
+        if (pass) crypto_add(aovs, a, i, true, pixel, s.inv_density, counters);
+      } else if (aovs.filter[a] == 1) {  // closest: depth key
+        if (pass) {
+          const float white[3] = {1.f, 1.f, 1.f};
+          add_to_buffer(aovs, a, pixel, aov_value(aovs, s, a, i, debug_val), 0.0f, depth, s.inv_density, white, sample_base + i);
+        }
+      } else {
+        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+        float w = 0.f;
+        if (pass) {  // (aov_value + 0) * filter_weight * white, per sample as add_to_buffer rounds it
+          const float4 v = aov_value(aovs, s, a, i, debug_val);
+          w = s.inv_density;
+          r = make_float4((v.x + 0.0f) * w * 1.f, (v.y + 0.0f) * w * 1.f, (v.z + 0.0f) * w * 1.f, (v.w + 0.0f) * w);
+        }
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+          const float tx = __shfl_down_sync(0xffffffffu, r.x, off), ty = __shfl_down_sync(0xffffffffu, r.y, off);
+          const float tz = __shfl_down_sync(0xffffffffu, r.z, off), tw = __shfl_down_sync(0xffffffffu, r.w, off);
+          const float ww = __shfl_down_sync(0xffffffffu, w, off);
+          if (lane + off < 32 && (above & ((1u << off) - 1u)) == 0u) {  // lane + off belongs to this lane's run
+            r.x += tx; r.y += ty; r.z += tz; r.w += tw; w += ww;
+          }
+        }
+        if (pass && head) {
+          if (aovs.role[a] == 1 /*RGBA*/) atomicAdd(aovs.weight + pixel, w);
+          atomicAdd(aovs.buffer[a] + pixel, r);
+        }
       }
     }
-    if (aovs.debug_samples) aovs.debug_samples[i] = (uint16_t)debug_val;
   }
   // append redistributed samples to the work list, one atomic per warp
   const unsigned mask = __ballot_sync(0xffffffffu, redistribute);
-  const int lane = threadIdx.x & 31;
   unsigned base = 0;
-  if (lane == 0 && mask) base = atomicAdd(&counters->work_count, (unsigned)__popc(mask));
+  if (lane == 0 && mask) {
+    base = atomicAdd(&counters->work_count, (unsigned)__popc(mask));
+    atomicAdd(&counters->redistributed, (unsigned long long)__popc(mask));
+  }
   base = __shfl_sync(0xffffffffu, base, 0);
   if (redistribute) {
     WorkItem w;
@@ -134,12 +174,8 @@ k_filter_classify(const __grid_constant__ FilterConsts fc, const __grid_constant
     w.csp[0] = csp[0]; w.csp[1] = csp[1]; w.csp[2] = csp[2];
     work[base + __popc(mask & ((1u << lane) - 1u))] = w;
   }
-  const unsigned amask = __ballot_sync(0xffffffffu, active);
-  if (lane == 0 && amask) {
-    atomicAdd(&counters->samples, (unsigned long long)__popc(amask));
-    atomicAdd(&counters->redistributed, (unsigned long long)__popc(mask));
-    atomicAdd(&counters->passthrough, (unsigned long long)__popc(amask & ~mask));
-  }
+  // (samples consumed and pass-through adds are counted on the host: three same-address reductions per warp here cost
+  // more than the rest of the kernel -- 3.1 M serialised L2 operations for a 33 M-sample batch)
 }
 
 cudaError_t launch_filter_classify(const FilterConsts &fc, const AovSet &aovs, const SampleIO &s, WorkItem *work,

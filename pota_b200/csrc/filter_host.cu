@@ -52,6 +52,7 @@ struct FilterState {
   int crypto_cache_stride = 0;
   FilterCounters *d_counters = nullptr;
   uint64_t sample_base = 0;
+  uint64_t samples_seen = 0;  // source samples handed to accumulate since lb_filter_begin
   // host-path staging
   char *stage = nullptr;
   size_t stage_bytes = 0;
@@ -201,6 +202,7 @@ int accumulate_device(lb_camera *c, FilterState *f, const lb_samples *S, cudaStr
                             cam_num_sms(c), stream));
   if (f->has_closest || f->has_debug_closest) CUF(launch_closest_gather(fc, A, io, f->sample_base, stream));
   f->sample_base += S->n;
+  f->samples_seen += S->n;
   return LB_OK;
 }
 
@@ -288,6 +290,7 @@ int lb_filter_begin(lb_camera *c, const lb_frame_desc *frame, int n_aov, const l
   CUF(cudaMemset(f->d_counters, 0, sizeof(FilterCounters)));
   if (!f->stream) CUF(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking));
   f->sample_base = 0;
+  f->samples_seen = 0;
   return LB_OK;
 }
 
@@ -376,8 +379,8 @@ int lb_filter_get_stats(lb_camera *c, lb_filter_stats *out) {
   CUF(cudaDeviceSynchronize());
   FilterCounters h;
   CUF(cudaMemcpy(&h, f->d_counters, sizeof h, cudaMemcpyDeviceToHost));
-  out->samples = h.samples; out->redistributed = h.redistributed; out->splats = h.splats;
-  out->attempts = h.attempts; out->passthrough = h.passthrough;
+  out->samples = f->samples_seen; out->redistributed = h.redistributed; out->splats = h.splats;
+  out->attempts = h.attempts; out->passthrough = f->samples_seen - h.redistributed;
   out->crypto_dropped = h.crypto_dropped;
   return LB_OK;
 }
