@@ -122,6 +122,28 @@ def test_empty_and_ragged_batches():
         assert torch.isfinite(out["dir"]).all()
 
 
+def test_ray_results_do_not_depend_on_the_batch_split(kernel_kind):
+    """The unrolled kernel traces rays j and j + ceil(n/2) of a call in one thread (packed FP32 lanes): a ray's result
+    must not depend on which ray it is paired with, i.e. on how the caller cuts its samples into calls."""
+    from pota_b200.camera import RAY_OUT_FIELDS, Camera
+
+    cam = Camera(po_params(fstop=1.4, focus_dist=50.0, lens_model=0), device=0)  # f/1.4: a good share of rays retries
+    assert cam.kernel_kind == kernel_kind
+    n = 20_001
+    ins = {k: v.cuda() for k, v in workloads.camera_samples(200, 101, 1, "cpu", 0, n, "linear").items()}
+    keys = ("sx", "sy", "dsx", "dsy", "lensx", "lensy")
+    whole = cam.create_rays(*[ins[k] for k in keys])
+    torch.cuda.synchronize()
+    assert (whole["tries"] > 0).float().mean() > 0.05
+    for cut in (1, 7_000, 10_001, 20_000):
+        a = cam.create_rays(*[ins[k][:cut].contiguous() for k in keys], ray_id_base=0)
+        b = cam.create_rays(*[ins[k][cut:].contiguous() for k in keys], ray_id_base=cut)
+        torch.cuda.synchronize()
+        for f in list(RAY_OUT_FIELDS) + ["tries"]:
+            got = torch.cat([a[f], b[f]], dim=-1)
+            assert torch.equal(got.view(torch.int32), whole[f].view(torch.int32)), (cut, f)
+
+
 def test_reverse_rays():
     from pota_b200.camera import Camera
 
