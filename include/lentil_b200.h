@@ -131,6 +131,8 @@ LB_API void lb_camera_params_default(lb_camera_params *p);
 LB_API int lb_lens_count(void);
 LB_API const char *lb_lens_name(int lens_model); /* LensModelNames, pota_cpp_lenses.h */
 LB_API const char *lb_last_error(void);
+/* "lentil_b200 <major>.<minor>.<patch> (sm_100a)".  0.2.0: lb_frame_desc, lb_samples and lb_filter_stats grew at their
+ * ends (cryptomatte); callers built against 0.1 must be recompiled. */
 LB_API const char *lb_version(void);
 
 /* node_initialize + node_update (lentil_camera.cpp:56-68): builds the camera on CUDA device

@@ -418,7 +418,7 @@ void lb_camera_params_default(lb_camera_params *p) {  // lentil_camera.cpp:19-52
 int lb_lens_count(void) { return LP_LENS_COUNT; }
 const char *lb_lens_name(int m) { return (m >= 0 && m < LP_LENS_COUNT) ? LP_LENSES[m].name : nullptr; }
 const char *lb_last_error(void) { return g_last_error.c_str(); }
-const char *lb_version(void) { return "lentil_b200 0.1.0 (sm_100a)"; }
+const char *lb_version(void) { return "lentil_b200 0.2.0 (sm_100a)"; }
 
 int lb_camera_create(const lb_camera_params *params, const lb_bokeh_image *bokeh, int device, lb_camera **out) {
   if (!params || !out) return fail(LB_ERR_INVALID, "null argument");
