@@ -24,7 +24,10 @@
 namespace lb {
 
 // lanes that must be waiting before the (divergent) service phase of the splat loop runs
-constexpr int kServiceBatch = 8;
+#ifndef LB_SERVICE_BATCH
+#define LB_SERVICE_BATCH 8
+#endif
+constexpr int kServiceBatch = LB_SERVICE_BATCH;
 
 // aperture point of attempt `total`, try `tries` (lentil.h:594-609)
 LB_DEV void bw_aperture_sample(const CamConsts<float> &cam, uint32_t seed_base, uint32_t total, int tries, float &ax, float &ay) {
