@@ -136,7 +136,7 @@ LB_DEV void pt_sample_aperture2(const E &ev, const float x[2], const float y[2],
     for (int h = 0; h < 2; ++h) {
       if (!(sqr_err[h] > 1e-4f)) continue;
       const float J0 = lo_hi(J[0], h), J1 = lo_hi(J[1], h), J2 = lo_hi(J[2], h), J3 = lo_hi(J[3], h);
-      const float invdet = 1.0f / (J0 * J3 - J1 * J2);
+      const float invdet = t_rcp(J0 * J3 - J1 * J2);
       const float e0 = ax[h] - lo_hi(ap[0], h), e1 = ay[h] - lo_hi(ap[1], h);
       dx[h] += (J3 * invdet) * e0;
       dx[h] += (-J1 * invdet) * e1;

@@ -51,9 +51,18 @@ template <> LB_DEV double t_sqrt<double>(double x) { return sqrt(x); }
 // as the host code.  float: rsqrtf (MUFU.RSQ, 2 ulp) -- the IEEE sqrt + IEEE divide pair is ~18 instructions with a
 // slow-path branch each, three times per lt_sample_aperture iteration: +4.9 % splats/s, +1 % rays/s, identical splat
 // counts, all parity bounds unchanged (2 ulp = 2.4e-7 relative against the 1e-4 bound).  -DLB_IEEE_RSQRT restores it.
+// The divisions follow the same rule: another +8.2 % splats/s and +3.7 % rays/s (profiles/r01_k2_knobs.txt).
 template <typename T> LB_DEV T t_rsqrt(T x) { return T(1) / t_sqrt(x); }
+// a / b and 1 / x of the same code and of the 2x2 Newton inverses.  float: MUFU.RCP based (__fdividef, 2 ulp) unless
+// -DLB_IEEE_RSQRT; -DLB_IEEE_DIV keeps only the divisions IEEE.
+template <typename T> LB_DEV T t_div(T a, T b) { return a / b; }
+template <typename T> LB_DEV T t_rcp(T x) { return T(1) / x; }
 #ifndef LB_IEEE_RSQRT
 template <> LB_DEV float t_rsqrt<float>(float x) { return rsqrtf(x); }
+#ifndef LB_IEEE_DIV
+template <> LB_DEV float t_div<float>(float a, float b) { return __fdividef(a, b); }
+template <> LB_DEV float t_rcp<float>(float x) { return __fdividef(1.0f, x); }
+#endif
 #endif
 template <typename T> LB_DEV T t_abs(T x) { return x < T(0) ? -x : x; }
 template <typename T> LB_DEV T t_max(T a, T b) { return a > b ? a : b; }
@@ -134,8 +143,8 @@ LB_DEV void bokeh_sample(const C &cam, float randomNumberRow, float randomNumber
 template <typename T>
 LB_DEV void sphere_to_cs(T px, T py, T dx, T dy, T R, T pos[3], T dir[3]) {
   const T r2 = px * px + py * py;
-  const T nx = px / R, ny = py / R;
-  const T nz = t_sqrt(t_max(T(0), R * R - r2)) / t_abs(R);
+  const T nx = t_div(px, R), ny = t_div(py, R);
+  const T nz = t_div(t_sqrt(t_max(T(0), R * R - r2)), t_abs(R));
   const T tz = t_sqrt(t_max(T(0), T(1) - dx * dx - dy * dy));
   // ex = normalise(nz, 0, -nx); ey = n x ex
   const T il = t_rsqrt(nz * nz + nx * nx);
@@ -147,7 +156,7 @@ LB_DEV void sphere_to_cs(T px, T py, T dx, T dy, T R, T pos[3], T dir[3]) {
   pos[0] = px;
   pos[1] = py;
   if (sizeof(T) == 8) pos[2] = nz * R + (-R);  // double path mirrors the reference expression
-  else pos[2] = -(r2 < R * R ? r2 : R * R) / (R * (nz + T(1)));  // R*(nz-1) = R*(nz^2-1)/(nz+1)
+  else pos[2] = t_div(-(r2 < R * R ? r2 : R * R), R * (nz + T(1)));  // R*(nz-1) = R*(nz^2-1)/(nz+1)
 }
 // general-centre variant (setup only: inner pupil, lentil.h:1423)
 template <typename T>
@@ -159,7 +168,7 @@ LB_DEV void sphere_to_cs_center(T px, T py, T dx, T dy, T center, T R, T pos[3],
 // csToSphere, lens.h:127-153
 template <typename T>
 LB_DEV void cs_to_sphere(const T pos[3], const T dir_in[3], T center, T R, T &odx, T &ody) {
-  const T nx = pos[0] / R, ny = pos[1] / R, nz = t_abs((pos[2] - center) / R);
+  const T nx = t_div(pos[0], R), ny = t_div(pos[1], R), nz = t_abs(t_div(pos[2] - center, R));
   const T dl = t_rsqrt(dir_in[0] * dir_in[0] + dir_in[1] * dir_in[1] + dir_in[2] * dir_in[2]);
   const T d0 = dir_in[0] * dl, d1 = dir_in[1] * dl, d2 = dir_in[2] * dl;
   const T il = t_rsqrt(nz * nz + nx * nx);
@@ -291,7 +300,7 @@ LB_DEV int pt_sample_aperture(const E &ev, T x, T y, T &dx, T &dy, T lambda, T a
     const T b[5] = {x + dist * dx, y + dist * dy, dx, dy, lambda};
     T ap[2], J[4];
     ev.ap_jac(b, ap, J);
-    const T invdet = T(1) / (J[0] * J[3] - J[1] * J[2]);
+    const T invdet = t_rcp(J[0] * J[3] - J[1] * J[2]);
     const T e0 = ax - ap[0], e1 = ay - ap[1];
     dx += (J[3] * invdet) * e0;
     dx += (-J[1] * invdet) * e1;
@@ -332,7 +341,7 @@ LB_DEV void lt_iterate_tail(const C &cam, const T scene[3], T ax, T ay, const T 
   const T prev_sqr_err = s.sqr_err, prev_sqr_ap_err = s.sqr_ap_err;
   const T da0 = ax - ap[0], da1 = ay - ap[1];
   s.sqr_ap_err = da0 * da0 + da1 * da1;
-  const T invdetap = T(1) / (J[0] * J[3] - J[1] * J[2]);
+  const T invdetap = t_rcp(J[0] * J[3] - J[1] * J[2]);
   s.dx += (J[3] * invdetap) * da0;
   s.dx += (-J[1] * invdetap) * da1;
   s.dy += (-J[2] * invdetap) * da0;
@@ -344,7 +353,7 @@ LB_DEV void lt_iterate_tail(const C &cam, const T scene[3], T ax, T ay, const T 
   cs_to_outer(cam, pos, view, ndx, ndy);
   const T do0 = ndx - s.out[2], do1 = ndy - s.out[3];
   s.sqr_err = do0 * do0 + do1 * do1;
-  const T invdet = T(1) / (K[0] * K[3] - K[1] * K[2]);
+  const T invdet = t_rcp(K[0] * K[3] - K[1] * K[2]);
   s.x += T(0.72) * (K[3] * invdet) * do0;
   s.x += T(0.72) * (-K[1] * invdet) * do1;
   s.y += T(0.72) * (-K[2] * invdet) * do0;
