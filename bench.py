@@ -298,6 +298,37 @@ def main():
         e2e_s = max_over_ranks(time.perf_counter() - t0)
         e2e = {"value": world * n_rays * e2e_steps / e2e_s, "unit": "rays/s", "h2d_bytes_per_step": n_rays * 24, "d2h_bytes_per_step": n_rays * 84,
                "ms_per_step": e2e_s / e2e_steps * 1e3, "calls_per_step": calls, "host_memory": "pinned", "matches_device_path": checked}
+        # what bounds it: the host link.  Plain pinned-memory copies of this box, device-to-host alone and with a
+        # host-to-device copy running beside it (the e2e path moves 84 B out and 24 B in per ray, full duplex)
+        nb = 256 << 20
+        hb0, hb1 = torch.empty(nb, dtype=torch.uint8).pin_memory(), torch.empty(nb, dtype=torch.uint8).pin_memory()
+        db0, db1 = torch.empty(nb, dtype=torch.uint8, device=dev), torch.empty(nb, dtype=torch.uint8, device=dev)
+        s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+        def copy_rate(duplex):
+            best = 0.0
+            for _ in range(3):
+                torch.cuda.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                with torch.cuda.stream(s1):
+                    a.record(s1)
+                    for _ in range(4):
+                        hb0.copy_(db0, non_blocking=True)
+                    b.record(s1)
+                if duplex:
+                    with torch.cuda.stream(s2):
+                        for _ in range(2):
+                            db1.copy_(hb1, non_blocking=True)
+                torch.cuda.synchronize()
+                best = max(best, 4 * nb / (a.elapsed_time(b) * 1e-3) / 1e9)
+            return best
+
+        d2h_alone, d2h_duplex = copy_rate(False), copy_rate(True)
+        achieved = n_rays * 84 * e2e_steps / e2e_s / 1e9
+        e2e["link"] = {"d2h_copy_gbs": d2h_alone, "d2h_copy_gbs_with_h2d_beside": d2h_duplex, "d2h_achieved_gbs_per_gpu": achieved,
+                       "frac_of_copy_rate": achieved / max(d2h_duplex, 1e-9),
+                       "note": "pinned 256 MiB cudaMemcpyAsync on this box; the e2e path is bound by the device-to-host direction"}
+        del hb0, hb1, db0, db1
         del h_in, h_out
     del ins, out
     torch.cuda.empty_cache()
