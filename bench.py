@@ -285,7 +285,7 @@ def main():
 
         # warm-up (allocates the staging ring) doubling as a check: the host path must reproduce the device path bit for bit
         cam.create_rays_host(*[h_in[k] for k in IN_KEYS], out=h_out, ray_id_base=first_sample)
-        checked = all(bool(torch.equal(h_out[k].to(dev), out[k][:, :chunk])) for k in ("origin", "dir", "dDdx", "weight"))
+        checked = all(bool(torch.equal(h_out[k].to(dev), out[k][:, :chunk])) for k in RAY_OUT_FIELDS)
         assert checked, "host path and device path disagree"
         barrier()
         t0 = time.perf_counter()
@@ -296,7 +296,9 @@ def main():
                 cam.create_rays_host(*[h_in[k][:m] for k in IN_KEYS], out=h_out, ray_id_base=first_sample + cidx * chunk)
         barrier()
         e2e_s = max_over_ranks(time.perf_counter() - t0)
-        e2e = {"value": world * n_rays * e2e_steps / e2e_s, "unit": "rays/s", "h2d_bytes_per_step": n_rays * 24, "d2h_bytes_per_step": n_rays * 84,
+        e2e = {"value": world * n_rays * e2e_steps / e2e_s, "unit": "rays/s", "h2d_bytes_per_step": n_rays * 24, "d2h_bytes_per_step": n_rays * 76,
+               "host_bytes_delivered_per_step": n_rays * 84,
+               "d2h_note": "84 B/ray land in the caller's buffers; 76 cross the link: the three weight channels are one number, planes 1-2 are filled on the host",
                "ms_per_step": e2e_s / e2e_steps * 1e3, "calls_per_step": calls, "host_memory": "pinned", "matches_device_path": checked}
         # what bounds it: the host link.  Plain pinned-memory copies of this box, device-to-host alone and with a
         # host-to-device copy running beside it (the e2e path moves 84 B out and 24 B in per ray, full duplex)
@@ -324,7 +326,7 @@ def main():
             return best
 
         d2h_alone, d2h_duplex = copy_rate(False), copy_rate(True)
-        achieved = n_rays * 84 * e2e_steps / e2e_s / 1e9
+        achieved = n_rays * 76 * e2e_steps / e2e_s / 1e9
         e2e["link"] = {"d2h_copy_gbs": d2h_alone, "d2h_copy_gbs_with_h2d_beside": d2h_duplex, "d2h_achieved_gbs_per_gpu": achieved,
                        "frac_of_copy_rate": achieved / max(d2h_duplex, 1e-9),
                        "note": "pinned 256 MiB cudaMemcpyAsync on this box; the e2e path is bound by the device-to-host direction"}

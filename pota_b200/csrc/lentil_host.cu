@@ -535,6 +535,17 @@ int lb_camera_create_rays_host(lb_camera *c, size_t n, uint64_t ray_id_base, con
   }
   const float *src[6] = {in->sx, in->sy, in->dsx, in->dsy, in->lensx, in->lensy};
   float *dst[7] = {out->origin, out->dir, out->dOdx, out->dOdy, out->dDdx, out->dDdy, out->weight};
+  // The three channels of `weight` are the same number (AtRGB white or black times the exposure, lentil.h:379,
+  // lentil_camera.cpp:124): only plane 0 crosses the host link (the path is bound by its device-to-host direction,
+  // 84 -> 76 B per ray), and this thread fills planes 1 and 2 from it while later chunks are in flight.
+  auto replicate_weight = [&](size_t kk) -> cudaError_t {
+    const size_t b = kk * chunk, m = std::min(chunk, n - b);
+    cudaError_t e = cudaEventSynchronize(c->pipe_event[kk % 3]);
+    if (e != cudaSuccess) return e;
+    memcpy(out->weight + n + b, out->weight + b, m * sizeof(float));
+    memcpy(out->weight + 2 * n + b, out->weight + b, m * sizeof(float));
+    return cudaSuccess;
+  };
   size_t k = 0;
   for (size_t base = 0; base < n; base += chunk, ++k) {
     const int s = (int)(k % 3);
@@ -550,11 +561,18 @@ int lb_camera_create_rays_host(lb_camera *c, size_t n, uint64_t ray_id_base, con
     io.tries = out->tries ? (int32_t *)(o + 21 * chunk) : nullptr;
     io.plane = chunk;
     CU(launch_rays(c, io, m, ray_id_base + base, st));
-    for (int v = 0; v < 7; ++v)
+    for (int v = 0; v < 6; ++v)
       if (dst[v])  // 3 planes of the chunk -> 3 plane ranges of the user's [3][n] array: one strided copy
         CU(cudaMemcpy2DAsync(dst[v] + base, n * sizeof(float), o + (size_t)v * 3 * chunk, chunk * sizeof(float), m * sizeof(float), 3,
                              cudaMemcpyDeviceToHost, st));
+    if (out->weight) CU(cudaMemcpyAsync(out->weight + base, io.weight, m * sizeof(float), cudaMemcpyDeviceToHost, st));
     if (out->tries) CU(cudaMemcpyAsync(out->tries + base, io.tries, m * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(c->pipe_event[s], st));
+    if (out->weight && k >= 2) CU(replicate_weight(k - 2));  // two chunks stay in flight behind this wait
+  }
+  if (out->weight) {
+    if (k >= 2) CU(replicate_weight(k - 2));
+    CU(replicate_weight(k - 1));
   }
   for (int i = 0; i < 3; ++i) CU(cudaStreamSynchronize(c->pipe_stream[i]));
   return LB_OK;
