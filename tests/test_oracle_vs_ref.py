@@ -368,3 +368,31 @@ def test_reverse_trace_on_reference_debug_positions(libs):
         hits += int(bool(ok1))
         assert O.orc_get_coc_thinlens(o._h, float(np.float32(P[2]))) == R.ref_get_coc_thinlens(r._h, float(np.float32(P[2])))
     assert hits > 3000
+
+
+@pytest.mark.parametrize("lens_model", range(44))
+def test_every_lens_forward_and_reverse(lens_model, libs):
+    """Lens-pack breadth: setup solvers, camera_create_ray and trace_ray_bw_po of the reference vs the oracle for each of
+    the 44 lens ids (the generated bodies differ per lens; the wrappers around them must not care)."""
+    O, R = libs
+    from pota_b200.lensgen.prescriptions import LENS_IDS
+    focal = float(LENS_IDS[lens_model].split("__")[-1].replace("mm", ""))
+    p = po_params(lens_model=lens_model, fstop=2.0, focus_dist=120.0, sensor_width=min(36.0, 0.7 * focal))
+    o, r = orc.OracleCamera(p), ref.RefCamera(p)
+    so, sr = o.state, r.state
+    assert (so.aperture_radius, so.sensor_shift, so.tan_fov) == (sr.aperture_radius, sr.sensor_shift, sr.tan_fov)
+    n = 1500
+    ins = workloads.camera_samples(50, 30, 1, "cpu", 0, n, "linear")
+    arrs = [ins[k].numpy() for k in ("sx", "sy", "dsx", "dsy", "lensx", "lensy")]
+    a, b = o.create_rays(*arrs), r.create_rays(*arrs)
+    first = a["tries"] == 0
+    assert first.mean() > 0.3
+    for k in orc.RAY_OUT_FIELDS:
+        np.testing.assert_array_equal(a[k][:, first], b[k][:, first], err_msg=k)
+    rs = np.random.default_rng(lens_model)
+    s1, s2 = (C.c_double * 2)(), (C.c_double * 2)()
+    for i in range(60):
+        tgt = (C.c_double * 3)(rs.uniform(-200, 200), rs.uniform(-120, 120), rs.uniform(300, 3000))
+        ok1 = O.orc_trace_ray_bw_po(o._h, tgt, 17 + i, 29 + 2 * i, i, C.c_float(0.55), s1)
+        ok2 = R.ref_trace_ray_bw_po(r._h, tgt, 17 + i, 29 + 2 * i, i, C.c_float(0.55), s2)
+        assert ok1 == ok2 and (not ok1 or list(s1) == list(s2)), i
