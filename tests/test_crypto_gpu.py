@@ -176,3 +176,39 @@ def test_cryptomatte_rejects_bad_arguments():
     zi = torch.zeros(n, dtype=torch.int32, device="cuda")
     with pytest.raises(LentilError):
         g.filter_accumulate(zi, zi, z, z, 1.0, crypto=dict(depth=9, opacity=torch.zeros((n, 9), device="cuda"), ids={1: torch.zeros((n, 9), device="cuda")}))
+
+
+def test_cryptomatte_render_region():
+    """Tables and ranked buckets inside a render region: bucket coordinates are frame coordinates (lentil_imager.cpp:116-120)."""
+    from oracle import orc
+    from pota_b200.camera import Camera
+
+    p = abi.CameraParams.defaults(camera_type=abi.LB_CAMERA_THINLENS, focal_length_lentil=50.0, fstop=1.4, focus_dist=35.0, bidir_sample_mult=6)
+    ocam, gcam = orc.OracleCamera(p), Camera(p, None, device=0)
+    Wf, Hf, spp = 96, 54, 9
+    x0, y0, W, H = 24, 12, 48, 30
+    fr = workloads.highlight_frame(Wf, Hf, spp, ocam.state.tan_fov, "cpu")
+    cr = workloads.crypto_layers(fr, 3, [1, 2])
+    px, py = fr["px"].numpy(), fr["py"].numpy()
+    m = (px >= x0) & (px < x0 + W) & (py >= y0) & (py < y0 + H)
+    crypto = dict(depth=3, count=cr["count"].numpy()[m], opacity=cr["opacity"].numpy()[m], ids={a: v.numpy()[m] for a, v in cr["ids"].items()})
+    args = (px[m] - x0, py[m] - y0, fr["rgba"].numpy()[m], fr["pos_cs"].numpy()[m], 1.0 / spp)
+    aovs = [("RGBA", 0, 1), ("crypto_object00", 2, 0), ("crypto_object01", 2, 0)]
+    ocam.filter_begin(W, H, aovs, xres_full=Wf, yres_full=Hf, region_min=(x0, y0))
+    ocam.filter_accumulate(*args, crypto=crypto)
+    gcam.filter_begin(W, H, aovs, xres_full=Wf, yres_full=Hf, region_min=(x0, y0))
+    gcam.filter_accumulate_host(*args, crypto=crypto)
+    for a in (1, 2):
+        palette = np.union1d(np.unique(cr["ids"][a].numpy()), np.float32([0.0]))
+        io, wo, to, _ = ocam.crypto(a, 32)
+        ig, wg, tg = gcam.crypto(a)
+        po, no = _planes(io, wo, palette)
+        pg, ng = _planes(ig, wg, palette)
+        np.testing.assert_array_equal(no, ng)
+        np.testing.assert_allclose(pg, po, rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(tg, to, rtol=1e-5, atol=1e-7)
+        for box in (dict(), dict(x0=x0 + 8, y0=y0 + 4, w=20, h=10)):
+            ro, rg = ocam.resolve(a, fill=-7.0, **box), gcam.resolve(a, fill=-7.0, **box).cpu().numpy()
+            np.testing.assert_array_equal(ro[..., 1] == -7.0, rg[..., 1] == -7.0)
+            agree = (ro[..., 0] == rg[..., 0]) & (np.abs(ro[..., 1] - rg[..., 1]) <= 2e-3)
+            assert agree.mean() > 0.995, agree.mean()

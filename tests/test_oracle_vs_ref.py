@@ -396,3 +396,31 @@ def test_every_lens_forward_and_reverse(lens_model, libs):
         ok1 = O.orc_trace_ray_bw_po(o._h, tgt, 17 + i, 29 + 2 * i, i, C.c_float(0.55), s1)
         ok2 = R.ref_trace_ray_bw_po(r._h, tgt, 17 + i, 29 + 2 * i, i, C.c_float(0.55), s2)
         assert ok1 == ok2 and (not ok1 or list(s1) == list(s2)), i
+
+
+def test_cryptomatte_render_region(libs):
+    """Cryptomatte tables and ranked buckets inside a render region (region_min != 0, lentil.h:1070-1080)."""
+    p = abi.CameraParams.defaults(camera_type=abi.LB_CAMERA_THINLENS, focal_length_lentil=50.0, fstop=1.4, focus_dist=35.0, bidir_sample_mult=6)
+    o, r = orc.OracleCamera(p), ref.RefCamera(p)
+    Wf, Hf, spp = 96, 54, 9
+    x0, y0, W, H = 24, 12, 48, 30
+    fr = workloads.highlight_frame(Wf, Hf, spp, o.state.tan_fov, "cpu")
+    cr = workloads.crypto_layers(fr, 3, [1, 2])
+    px, py = fr["px"].numpy(), fr["py"].numpy()
+    m = (px >= x0) & (px < x0 + W) & (py >= y0) & (py < y0 + H)
+    crypto = dict(depth=3, count=cr["count"].numpy()[m], opacity=cr["opacity"].numpy()[m], ids={a: v.numpy()[m] for a, v in cr["ids"].items()})
+    args = (px[m] - x0, py[m] - y0, fr["rgba"].numpy()[m], fr["pos_cs"].numpy()[m], 1.0 / spp)
+    aovs = [("RGBA", 0, 1), ("crypto_object00", 2, 0), ("crypto_object01", 2, 0)]
+    o.filter_begin(W, H, aovs, xres_full=Wf, yres_full=Hf, region_min=(x0, y0))
+    o.filter_accumulate(*args, crypto=crypto)
+    r.filter_begin(W, H, aovs, xres_full=Wf, yres_full=Hf, region_min=(x0, y0), spp=spp)
+    r.filter_accumulate(*args, crypto=crypto)
+    for a in (1, 2):
+        io, wo, to, mo = o.crypto(a, 32)
+        ir, wr, tr, mr = r.crypto(a, 32)
+        assert mo == mr
+        np.testing.assert_array_equal(io.view(np.uint32), ir.view(np.uint32))
+        np.testing.assert_array_equal(wo, wr)
+        np.testing.assert_array_equal(to, tr)
+        for box in (dict(), dict(x0=x0 + 8, y0=y0 + 4, w=20, h=10)):
+            np.testing.assert_array_equal(o.resolve(a, fill=-7.0, **box).view(np.uint32), r.resolve(a, fill=-7.0, **box).view(np.uint32))
