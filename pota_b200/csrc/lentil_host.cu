@@ -538,8 +538,18 @@ int lb_camera_create_rays_host(lb_camera *c, size_t n, uint64_t ray_id_base, con
   // The three channels of `weight` are the same number (AtRGB white or black times the exposure, lentil.h:379,
   // lentil_camera.cpp:124): only plane 0 crosses the host link (the path is bound by its device-to-host direction,
   // 84 -> 76 B per ray), and this thread fills planes 1 and 2 from it while later chunks are in flight.
+  // chunk schedule: a long call ramps up with chunk/8, chunk/4, chunk/2 so the first device-to-host copy starts early
+  std::vector<size_t> starts, sizes;
+  for (size_t b = 0; b < n;) {
+    size_t m = chunk;
+    if (n > 4 * chunk && starts.size() < 3) m = chunk >> (3 - starts.size());
+    m = std::min(m, n - b);
+    starts.push_back(b);
+    sizes.push_back(m);
+    b += m;
+  }
   auto replicate_weight = [&](size_t kk) -> cudaError_t {
-    const size_t b = kk * chunk, m = std::min(chunk, n - b);
+    const size_t b = starts[kk], m = sizes[kk];
     cudaError_t e = cudaEventSynchronize(c->pipe_event[kk % 3]);
     if (e != cudaSuccess) return e;
     memcpy(out->weight + n + b, out->weight + b, m * sizeof(float));
@@ -547,9 +557,9 @@ int lb_camera_create_rays_host(lb_camera *c, size_t n, uint64_t ray_id_base, con
     return cudaSuccess;
   };
   size_t k = 0;
-  for (size_t base = 0; base < n; base += chunk, ++k) {
+  for (; k < starts.size(); ++k) {
     const int s = (int)(k % 3);
-    const size_t m = std::min(chunk, n - base);
+    const size_t base = starts[k], m = sizes[k];
     cudaStream_t st = c->pipe_stream[s];
     float *d = c->d_stage[s];
     for (int a = 0; a < 6; ++a) CU(cudaMemcpyAsync(d + a * chunk, src[a] + base, m * sizeof(float), cudaMemcpyHostToDevice, st));
