@@ -83,7 +83,7 @@ PACKED_ORDER = os.environ.get("LB_PACKED_ORDER", "lex")  # grouped | degree | le
 SCALAR_ORDER = os.environ.get("LB_SCALAR_ORDER", "lex")
 
 
-def _emit_streamed(lines, polys, outputs, packed=True, order=None):
+def _emit_streamed(lines, polys, outputs, packed=True, order=None, acc=2):
     """Body with every monomial consumed right after it is formed (short live ranges: the packed values take two
     registers each).  Accumulation order per polynomial therefore follows the monomial order, not the term order."""
     order = order or PACKED_ORDER
@@ -99,7 +99,7 @@ def _emit_streamed(lines, polys, outputs, packed=True, order=None):
                 uses.setdefault(tuple(e), []).append((j, c))
     consts = [sum(c for c, e in terms if sum(e) == 0) for terms in polys]
     nterms = [sum(1 for c, e in terms if sum(e) > 0) for terms in polys]
-    n_acc = [2 if n >= 12 else 1 for n in nterms]
+    n_acc = [acc if n >= 12 else 1 for n in nterms]
     started = [[False, False] for _ in polys]
     count = [0] * len(polys)
     names = [out.replace("[", "").replace("]", "").replace("*", "") for out in outputs]
@@ -151,7 +151,7 @@ def _emit_streamed(lines, polys, outputs, packed=True, order=None):
     return lines, dag.muls, ffma
 
 
-def emit_group(name, signature, polys, outputs, packed=False):
+def emit_group(name, signature, polys, outputs, packed=False, acc=2):
     """One device function evaluating `polys` (list of term lists) at point b, writing `outputs` (lvalues).
 
     packed: every value is a float2 holding the same quantity of TWO independent evaluation points, every operation the
@@ -160,7 +160,7 @@ def emit_group(name, signature, polys, outputs, packed=False):
     ty = "float2" if packed else "float"
     lines = ["  LB_DEV void %s(%s) const {" % (name, signature), "    const %s b0 = b[0], b1 = b[1], b2 = b[2], b3 = b[3], b4 = b[4];" % ty]
     if packed and PACKED_ORDER != "grouped":
-        return _emit_streamed(lines, polys, outputs)
+        return _emit_streamed(lines, polys, outputs, acc=acc)
     if not packed and SCALAR_ORDER != "grouped":
         return _emit_streamed(lines, polys, outputs, packed=False, order=SCALAR_ORDER)
     dag = Dag(lines, "m", packed)
@@ -219,7 +219,7 @@ def lens_unit(lens) -> tuple[str, dict]:
     dap = [d("ap_x", 2), d("ap_x", 3), d("ap_y", 2), d("ap_y", 3)]
     dout = [d("out_dx", 0), d("out_dx", 1), d("out_dy", 0), d("out_dy", 1)]
     src = ["// generated by pota_b200.lensgen.emit_cuda from pota_b200/lenses/%s.json -- do not edit" % lens["lens_id"],
-           '#include "../camera_kernels.cuh"', '#include "../filter_kernels.cuh"', '#include "../unrolled_dispatch.h"', "",
+           '#include "../camera_kernels.cuh"', '#include "../filter_kernels%s.cuh"' % ("_packed" if K2_PACKED else ""), '#include "../unrolled_dispatch.h"', "",
            "namespace lb {", "namespace {", "", "struct Eval%d {" % k]
     stats = {}
     body, mul, ffma = emit_group("ap_jac", "const float b[5], float ap[2], float J[4]", [P["ap_x"], P["ap_y"]] + dap,
@@ -245,6 +245,12 @@ def lens_unit(lens) -> tuple[str, dict]:
                                  ["ap[0]", "ap[1]", "J[0]", "J[1]", "J[2]", "J[3]", "out[0]", "out[1]", "out[2]", "out[3]", "K[0]", "K[1]", "K[2]", "K[3]"])
     src += body
     stats["lt_all"] = (mul, ffma)
+    if K2_PACKED:  # experimental two-slot kernel (csrc/filter_kernels_packed.cuh)
+        body, _, _ = emit_group("lt_all2", "const float2 b[5], float2 ap[2], float2 J[4], float2 out[4], float2 K[4]",
+                                [P["ap_x"], P["ap_y"]] + dap + [P["out_x"], P["out_y"], P["out_dx"], P["out_dy"]] + dout,
+                                ["ap[0]", "ap[1]", "J[0]", "J[1]", "J[2]", "J[3]", "out[0]", "out[1]", "out[2]", "out[3]", "K[0]", "K[1]", "K[2]", "K[3]"],
+                                packed=True, acc=PACKED_ACC)
+        src += body
     src += ["};", "",
             "__global__ void __launch_bounds__(128%s)" % K1_MIN_BLOCKS,
             "k_create_rays_%d(const __grid_constant__ CamConsts<float> cam, const __grid_constant__ RayIO io, size_t n, uint64_t ray_id_base) {" % k,
@@ -255,7 +261,7 @@ def lens_unit(lens) -> tuple[str, dict]:
             "__global__ void __launch_bounds__(128%s)" % K2_MIN_BLOCKS,
             "k_filter_splat_%d(const __grid_constant__ CamConsts<float> cam, const __grid_constant__ FilterConsts fc, const __grid_constant__ AovSet aovs," % k,
             "                  const __grid_constant__ SampleIO s, const WorkItem *__restrict__ work, FilterCounters *__restrict__ counters, uint64_t sample_base) {",
-            "  splat_persistent(Eval%d{}, cam, fc, aovs, s, work, counters, sample_base);" % k,
+            "  splat_persistent%s(Eval%d{}, cam, fc, aovs, s, work, counters, sample_base);" % ("2" if K2_PACKED else "", k),
             "}", "", "}  // namespace", "",
             "cudaError_t launch_fw_lens_%d(const CamConsts<float> &cam, const RayIO &io, size_t n, uint64_t ray_id_base, cudaStream_t stream) {" % k,
             "  k_create_rays_%d<<<(unsigned)(((n + 1) / 2 + 127) / 128), 128, 0, stream>>>(cam, io, n, ray_id_base);" % k,
@@ -274,6 +280,8 @@ def lens_unit(lens) -> tuple[str, dict]:
 # the lexicographic bodies 7.01e8 at 4, 7.43e8 at 5 (96 registers, no spill), 7.44e8 at 6 (80, spills).
 K1_MIN_BLOCKS = ", " + os.environ.get("LB_K1_MINBLOCKS", "4")
 K2_MIN_BLOCKS = ", " + os.environ.get("LB_K2_MINBLOCKS", "5")
+K2_PACKED = os.environ.get("LB_K2_PACKED", "0") == "1"  # experimental, see csrc/filter_kernels_packed.cuh
+PACKED_ACC = int(os.environ.get("LB_PACKED_ACC", "2"))  # accumulators per long polynomial of lt_all2 (register pressure knob)
 
 
 def emit_cuda(out_dir: str, only=None):
