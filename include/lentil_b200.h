@@ -51,7 +51,7 @@ enum { LB_CAMERA_THINLENS = 0, LB_CAMERA_POLYNOMIAL_OPTICS = 1 };
 /* Node parameters of lentil_camera (lentil_camera.cpp:19-52), read as in lentil.h:1189-1243.
  * lb_camera_params_default() fills the reference's C++ defaults. */
 typedef struct lb_camera_params {
-  int32_t camera_type;       /* LB_CAMERA_*; only POLYNOMIAL_OPTICS is traced, ThinLens only feeds get_coc_thinlens */
+  int32_t camera_type;       /* LB_CAMERA_*: both models are traced (ThinLens is the reference's default, lentil_camera.cpp:20) */
   int32_t bidir_sample_mult; /* 5 */
   int32_t units;             /* LB_UNITS_*  ("automatic" must be resolved by the caller, lentil.h:1193-1199) */
   float sensor_width;        /* 36 */
@@ -132,7 +132,8 @@ LB_API int lb_lens_count(void);
 LB_API const char *lb_lens_name(int lens_model); /* LensModelNames, pota_cpp_lenses.h */
 LB_API const char *lb_last_error(void);
 /* "lentil_b200 <major>.<minor>.<patch> (sm_100a)".  0.2.0: lb_frame_desc, lb_samples and lb_filter_stats grew at their
- * ends (cryptomatte); callers built against 0.1 must be recompiled. */
+ * ends (cryptomatte); 0.3.0: lb_samples grew at its end (world_to_camera).  Callers built against an older minor must be
+ * recompiled. */
 LB_API const char *lb_version(void);
 
 /* node_initialize + node_update (lentil_camera.cpp:56-68): builds the camera on CUDA device
@@ -213,8 +214,11 @@ typedef struct lb_samples {
   size_t n;
   const int32_t *px, *py;   /* pixel the sample is filtered for, region-relative (:96-100) */
   const float *rgba;        /* [n][4] RGBA AOV (:115) */
-  const float *pos_cs;      /* [n][4] camera-space position xyz BEFORE unit scaling (:142), w = Z depth AOV (:117) */
-  const float *raydir;      /* [n][4] lentil_raydir AOV, nullable (skydome only, :121-128) */
+  const float *pos_cs;      /* [n][4] xyz = the P AOV (:116), w = Z depth AOV (:117).  P is WORLD space when
+                               world_to_camera is given -- the device then does what :121-142 does: AiV3IsSmall on the
+                               world-space P, skydome substitution in world space, AiM4PointByMatrixMult.  With
+                               world_to_camera == NULL (identity) P is the camera-space position before unit scaling. */
+  const float *raydir;      /* [n][4] lentil_raydir AOV (same space as P), nullable (skydome only, :121-128) */
   const float *transmission;/* [n][4] transmission AOV, nullable (:152-159) */
   const uint32_t *flags;    /* LB_SAMPLE_* bits, nullable */
   const float *const *aov_values; /* [n_aov] device pointers to [n][4] values already widened to RGBA (:206-234);
@@ -227,6 +231,9 @@ typedef struct lb_samples {
   const float *crypto_opacity;    /* [n][D] AiColorToGrey(opacity AOV) of each sub-sample (:790) */
   const float *const *crypto_ids; /* [n_aov] device pointers to [n][D] hash ids of that AOV (:791); NULL entries for
                                      the other AOVs */
+  /* AiWorldToCameraMatrix of the batch (lentil_filter.cpp:139-142): HOST pointer (also in the device-pointer call) to an
+   * AtMatrix, float[4][4] row-major, row-vector convention p' = p * M as AiM4PointByMatrixMult; NULL = identity. */
+  const float *world_to_camera;
 } lb_samples;
 enum { LB_SAMPLE_VOLUME = 1u, LB_SAMPLE_IGNORE = 2u }; /* volume_in_sample (:136), lentil_bidir_ignore > 0 (:162) */
 
@@ -242,8 +249,11 @@ typedef struct lb_filter_stats {
 /* setup_filter (lentil.h:1056-1117): allocates zeroed device framebuffers. */
 LB_API int lb_filter_begin(lb_camera *cam, const lb_frame_desc *frame, int n_aov, const lb_aov_desc *aovs);
 /* filter_pixel, RGBA branch, for a batch of samples: classify, reverse trace, splat. */
+/* Calls on one camera execute in call order even when they are issued on different streams (they share the work list and
+ * the planes): each waits on the device for the previous accumulate / reduce / resolve of that camera. */
 LB_API int lb_filter_accumulate(lb_camera *cam, const lb_samples *samples, lb_stream stream);
-/* Same with every pointer in lb_samples (and aov_values[i]) a HOST pointer. */
+/* Same with every pointer in lb_samples (and aov_values[i]) a HOST pointer (pinned or pageable): the samples travel in
+ * chunks through two device staging blocks, the copy of one chunk beside the kernels of the previous one. */
 LB_API int lb_filter_accumulate_host(lb_camera *cam, const lb_samples *samples);
 LB_API int lb_filter_get_stats(lb_camera *cam, lb_filter_stats *out); /* synchronises */
 /* Diagnostic: lt_sample_aperture Newton iterations executed since lb_filter_begin (synchronises). */
@@ -254,6 +264,9 @@ LB_API int lb_filter_newton_iterations(lb_camera *cam, uint64_t *out);
  * bucket row that holds <= rank ids ends that row: it and the pixels after it are left as the caller
  * supplied them, so rgba_out is read-modify-write for these AOVs. */
 LB_API int lb_imager_resolve(lb_camera *cam, int aov, int x0, int y0, int w, int h, float *rgba_out, lb_stream stream);
+/* HOST bucket.  Meant to be called per bucket and output like driver_process_bucket: the first call after the frame
+ * changed resolves the whole region of that AOV into pinned host memory (one kernel, one copy), every call copies its
+ * bucket out of it -- no device work, allocation or synchronisation per bucket. */
 LB_API int lb_imager_resolve_host(lb_camera *cam, int aov, int x0, int y0, int w, int h, float *rgba_out);
 /* Raw accumulators (device pointers owned by the camera): AOVData::buffer [yres][xres][4],
  * filter_weight_buffer [yres][xres].  For a cryptomatte AOV the plane's x component is
@@ -279,6 +292,19 @@ LB_API int lb_comm_unique_id(uint8_t id_out[128]);
 LB_API int lb_comm_init(lb_camera *cam, int world_size, int rank, const uint8_t id[128]);
 LB_API int lb_filter_set_sample_base(lb_camera *cam, uint64_t first_global_sample_index);
 LB_API int lb_filter_reduce(lb_camera *cam, int root, lb_stream stream);
+/* The same combine in its scalable form: after the closest-key and cryptomatte steps, one in-place
+ * ncclReduceScatter per plane (all planes in one NCCL group), so every rank ends up OWNING one contiguous pixel slab of
+ * every plane -- lb_filter_slab tells which.  The planes are padded to a multiple of 5040 pixels so that 1..10, 12, 14,
+ * 15 and 16 ranks get equal slabs; other world sizes, and frames with cryptomatte AOVs (their ranked resolve reads
+ * whole bucket rows), return LB_ERR_INVALID: use lb_filter_reduce.  Outside its slab a
+ * rank's planes are partial afterwards: lb_imager_resolve refuses, lb_imager_resolve_gather is the resolve. */
+LB_API int lb_filter_reduce_scatter(lb_camera *cam, lb_stream stream);
+LB_API int lb_filter_slab(lb_camera *cam, size_t *first_pixel, size_t *n_pixels);
+/* driver_process_bucket (lentil_imager.cpp:112-189) for the whole region, after lb_filter_reduce_scatter: every rank
+ * resolves its own slab, the resolved slabs are gathered on `root` (ncclSend/ncclRecv) or on every rank (root < 0,
+ * ncclAllGather).  rgba_out: device [yres][xres][4], may be NULL on ranks that do not receive.  With a single rank (no
+ * communicator) it is a plain full-region resolve. */
+LB_API int lb_imager_resolve_gather(lb_camera *cam, int aov, float *rgba_out, int root, lb_stream stream);
 LB_API int lb_comm_destroy(lb_camera *cam);
 
 #ifdef __cplusplus

@@ -932,10 +932,10 @@ struct orc_camera {
     const float inverse_sample_density = S->inv_density;
     bool redistribute = true;
     float sample[4] = {S->rgba[4 * i], S->rgba[4 * i + 1], S->rgba[4 * i + 2], S->rgba[4 * i + 3]};
-    // camera-space position: the harness supplies world_to_camera * P directly (lentil_filter.cpp:139-142)
+    // sample_pos_ws (:116): world space when the batch carries a world_to_camera matrix, else camera space (identity)
     float csp[3] = {S->pos_cs[4 * i], S->pos_cs[4 * i + 1], S->pos_cs[4 * i + 2]};
     double depth = S->pos_cs[4 * i + 3];
-    // :119-133 AiV3IsSmall is evaluated on the world-space P; with an identity camera matrix that is csp
+    // :119-133 AiV3IsSmall is evaluated on the world-space P
     bool small = std::abs(csp[0]) < AI_EPSILON_F && std::abs(csp[1]) < AI_EPSILON_F && std::abs(csp[2]) < AI_EPSILON_F;
     if ((depth == AI_INFINITE_F || small) && enable_skydome) {
       float rd[3] = {0, 0, 0};
@@ -946,6 +946,13 @@ struct orc_camera {
     if ((depth == AI_INFINITE_F || small) && !enable_skydome) redistribute = false;
     const uint32_t flags = S->flags ? S->flags[i] : 0u;
     if (flags & LB_SAMPLE_VOLUME) redistribute = false;  // :135-137
+    if (S->world_to_camera) {  // :141-142 AiM4PointByMatrixMult(world_to_camera_matrix, sample_pos_ws), float, left to right
+      const float *m = S->world_to_camera;
+      const float x = csp[0], y = csp[1], z = csp[2];
+      csp[0] = x * m[0] + y * m[4] + z * m[8] + m[12];
+      csp[1] = x * m[1] + y * m[5] + z * m[9] + m[13];
+      csp[2] = x * m[2] + y * m[6] + z * m[10] + m[14];
+    }
     switch (unitModel) {  // :143-148
       case LB_UNITS_MM: for (float &v : csp) v *= (float)0.1; break;
       case LB_UNITS_CM: for (float &v : csp) v *= (float)1.0; break;
@@ -1283,13 +1290,15 @@ int orc_camera_set_state(orc_camera *c, double aperture_radius, double sensor_sh
 }
 
 // camera_create_ray over a batch; HOST pointers; nthreads > 1 splits the batch statically.
+// seed word of a 64-bit global ray index, as the product mixes it (csrc/lens_device.cuh ray_seed_word; deviation of the retry RNG)
+static inline uint32_t ray_seed_word(uint64_t id) { return (uint32_t)id ^ ((uint32_t)(id >> 32) * 0x9E3779B9u); }
 int orc_camera_create_rays(orc_camera *cam, size_t n, uint64_t ray_id_base, const lb_ray_in *in, const lb_ray_out *out, int nthreads) {
   if (!cam || !in || !out) return LB_ERR_INVALID;
   auto work = [&](orc_camera *c, size_t lo, size_t hi) {
     for (size_t i = lo; i < hi; ++i) {
       float o[21];
       int tries = 0;
-      c->camera_create_ray(in->sx[i], in->sy[i], in->dsx[i], in->dsy[i], in->lensx[i], in->lensy[i], (uint32_t)(ray_id_base + i), o, &tries);
+      c->camera_create_ray(in->sx[i], in->sy[i], in->dsx[i], in->dsy[i], in->lensx[i], in->lensy[i], ray_seed_word(ray_id_base + i), o, &tries);
       float *dst[7] = {out->origin, out->dir, out->dOdx, out->dOdy, out->dDdx, out->dDdy, out->weight};
       for (int v = 0; v < 7; ++v)
         if (dst[v]) { dst[v][i] = o[3 * v]; dst[v][n + i] = o[3 * v + 1]; dst[v][2 * n + i] = o[3 * v + 2]; }

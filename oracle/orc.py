@@ -141,8 +141,9 @@ class OracleCamera:
         rc = lib().orc_filter_begin(self._h, C.byref(self._frame), len(aovs), arr)
         assert rc == 0, rc
 
-    def filter_accumulate(self, px, py, rgba, pos_cs, inv_density, aov_values=None, raydir=None, transmission=None, flags=None, nthreads=1, crypto=None):
-        S, _keep = abi.host_samples(self._naov, px, py, rgba, pos_cs, inv_density, aov_values, raydir, transmission, flags, crypto)
+    def filter_accumulate(self, px, py, rgba, pos_cs, inv_density, aov_values=None, raydir=None, transmission=None, flags=None, nthreads=1, crypto=None,
+                          world_to_camera=None):
+        S, _keep = abi.host_samples(self._naov, px, py, rgba, pos_cs, inv_density, aov_values, raydir, transmission, flags, crypto, world_to_camera)
         rc = lib().orc_filter_accumulate(self._h, C.byref(S), nthreads)
         assert rc == 0, rc
 

@@ -229,6 +229,8 @@ int ref_filter_begin(ref_camera *r, const lb_frame_desc *f, int n_aov, const lb_
 // sample density from the number of samples it is handed (lentil_filter.cpp:79-87)
 int ref_filter_accumulate(ref_camera *r, const lb_samples *S, int nthreads) {
   shim_default_universe() = &r->uni;
+  r->camera.world_to_camera = AtMatrix();
+  if (S->world_to_camera) memcpy(r->camera.world_to_camera.data, S->world_to_camera, 16 * sizeof(float));
   const size_t n = S->n;
   std::vector<float> Z(4 * n), P(4 * n), vol(4 * n, 0.f), ign(4 * n, 0.f), zero(4 * n, 0.f);
   for (size_t i = 0; i < n; ++i) {

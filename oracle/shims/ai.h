@@ -182,6 +182,7 @@ struct AtNode {
   std::map<std::string, AtParamValueShim> params;
   void *local_data = nullptr;
   AtUniverse *universe = nullptr;
+  AtMatrix world_to_camera;  // camera nodes: what AiWorldToCameraMatrix returns (identity unless the harness sets it)
 };
 struct AtRenderSession { int dummy; };
 struct AtUniverse {
@@ -243,7 +244,7 @@ inline float AiCameraGetShutterEnd() { return 0.f; }
 inline void AiCameraInitialize(AtNode *) {}
 inline void AiCameraUpdate(AtNode *, bool) {}
 inline void AiCameraToWorldMatrix(const AtNode *, float, AtMatrix &m) { m = AtMatrix(); }
-inline void AiWorldToCameraMatrix(const AtNode *, float, AtMatrix &m) { m = AtMatrix(); }
+inline void AiWorldToCameraMatrix(const AtNode *n, float, AtMatrix &m) { m = n ? n->world_to_camera : AtMatrix(); }
 inline void AiFilterInitialize(AtNode *, bool, const char **) {}
 inline void AiFilterUpdate(AtNode *, float) {}
 inline void AiDriverInitialize(AtNode *, bool) {}

@@ -144,6 +144,7 @@ class Samples(C.Structure):
         ("crypto_count", C.c_void_p),
         ("crypto_opacity", C.c_void_p),
         ("crypto_ids", C.POINTER(C.c_void_p)),
+        ("world_to_camera", C.c_void_p),
     ]
 
 
@@ -151,7 +152,8 @@ class FilterStats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("samples", "redistributed", "splats", "attempts", "passthrough", "crypto_dropped")]
 
 
-def host_samples(n_aov, px, py, rgba, pos_cs, inv_density, aov_values=None, raydir=None, transmission=None, flags=None, crypto=None):
+def host_samples(n_aov, px, py, rgba, pos_cs, inv_density, aov_values=None, raydir=None, transmission=None, flags=None, crypto=None,
+                 world_to_camera=None):
     """lb_samples over HOST numpy arrays -> (Samples, keepalive list).
 
     crypto: dict(depth=D, opacity=[n][D] float32, ids={aov index: [n][D] float32}, count=[n] uint8 or None).
@@ -187,4 +189,6 @@ def host_samples(n_aov, px, py, rgba, pos_cs, inv_density, aov_values=None, rayd
         S.crypto_opacity = ptr(crypto.get("opacity"), np.float32)
         S.crypto_ids = ci
         keep.append(ci)
+    if world_to_camera is not None:
+        S.world_to_camera = ptr(np.asarray(world_to_camera, np.float32).reshape(4, 4), np.float32)
     return S, keep

@@ -30,6 +30,7 @@ EXPORTS = [
     "lb_filter_begin", "lb_filter_accumulate", "lb_filter_accumulate_host", "lb_filter_get_stats",
     "lb_filter_newton_iterations", "lb_imager_resolve", "lb_imager_resolve_host", "lb_filter_buffers", "lb_filter_buffers_host", "lb_filter_crypto_host",
     "lb_bench_fp32_peak", "lb_bench_red_peak", "lb_camera_set_pupil_geometry", "lb_camera_kernel_kind", "lb_comm_unique_id", "lb_comm_init", "lb_filter_set_sample_base", "lb_filter_reduce", "lb_comm_destroy",
+    "lb_filter_reduce_scatter", "lb_filter_slab", "lb_imager_resolve_gather",
 ]  # fmt: skip
 
 
@@ -79,6 +80,9 @@ def lib():
         L.lb_filter_set_sample_base.argtypes = [vp, u64]
         L.lb_filter_reduce.argtypes = [vp, i, vp]
         L.lb_comm_destroy.argtypes = [vp]
+        L.lb_filter_reduce_scatter.argtypes = [vp, vp]
+        L.lb_filter_slab.argtypes = [vp, C.POINTER(sz), C.POINTER(sz)]
+        L.lb_imager_resolve_gather.argtypes = [vp, i, vp, i, vp]
         _lib = L
     return _lib
 
@@ -129,6 +133,7 @@ class Camera:
         _check(lib().lb_camera_create(C.byref(params), C.byref(img) if img is not None else None, device, C.byref(self._h)))
         self._frame = None
         self._aovs = []
+        self._rank = 0
 
     def close(self):
         if getattr(self, "_h", None):
@@ -209,7 +214,7 @@ class Camera:
         self._aovs = list(aovs)
         _check(lib().lb_filter_begin(self._h, C.byref(self._frame), len(aovs), arr))
 
-    def _samples(self, px, py, rgba, pos_cs, inv_density, aov_values, raydir, transmission, flags, ptr, crypto=None):
+    def _samples(self, px, py, rgba, pos_cs, inv_density, aov_values, raydir, transmission, flags, ptr, crypto=None, world_to_camera=None):
         n = int(px.shape[0])
         av = (C.c_void_p * max(len(self._aovs), 1))()
         for k in range(len(self._aovs)):
@@ -227,16 +232,22 @@ class Camera:
             S.crypto_opacity = ptr(crypto.get("opacity"))
             S.crypto_ids = ci
             keep.append(ci)
+        if world_to_camera is not None:  # AtMatrix, float32 [4, 4] row-major on the HOST (lentil_filter.cpp:139-142)
+            m = np.ascontiguousarray(np.asarray(world_to_camera, np.float32).reshape(4, 4))
+            S.world_to_camera = C.c_void_p(m.ctypes.data)
+            keep.append(m)
         return S, keep
 
     def filter_accumulate(self, px, py, rgba, pos_cs, inv_density, aov_values=None, raydir=None, transmission=None, flags=None, stream=None,
-                          crypto=None):
-        """filter_pixel (RGBA branch) for a device-resident batch of samples."""
-        S, keep = self._samples(px, py, rgba, pos_cs, inv_density, aov_values, raydir, transmission, flags, _dptr, crypto)
+                          crypto=None, world_to_camera=None):
+        """filter_pixel (RGBA branch) for a device-resident batch of samples.  world_to_camera: AtMatrix [4, 4] on the host;
+        pos_cs / raydir are then world space (the device applies lentil_filter.cpp:121-142)."""
+        S, keep = self._samples(px, py, rgba, pos_cs, inv_density, aov_values, raydir, transmission, flags, _dptr, crypto, world_to_camera)
         _check(lib().lb_filter_accumulate(self._h, C.byref(S), _stream_ptr(stream)))
 
-    def filter_accumulate_host(self, px, py, rgba, pos_cs, inv_density, aov_values=None, raydir=None, transmission=None, flags=None, crypto=None):
-        S, keep = self._samples(px, py, rgba, pos_cs, inv_density, aov_values, raydir, transmission, flags, _hptr, crypto)
+    def filter_accumulate_host(self, px, py, rgba, pos_cs, inv_density, aov_values=None, raydir=None, transmission=None, flags=None, crypto=None,
+                               world_to_camera=None):
+        S, keep = self._samples(px, py, rgba, pos_cs, inv_density, aov_values, raydir, transmission, flags, _hptr, crypto, world_to_camera)
         _check(lib().lb_filter_accumulate_host(self._h, C.byref(S)))
 
     def filter_stats(self) -> dict:
@@ -262,11 +273,16 @@ class Camera:
         _check(lib().lb_imager_resolve(self._h, aov, x0, y0, w, h, _dptr(out), _stream_ptr(stream)))
         return out
 
-    def resolve_host(self, aov: int, out: np.ndarray | None = None):
+    def resolve_host(self, aov: int, out: np.ndarray | None = None, x0=None, y0=None, w=None, h=None):
+        """driver_process_bucket with a host bucket (default: the whole region); `out` is [h, w, 4] float32."""
         f = self._frame
+        x0 = f.region_min_x if x0 is None else x0
+        y0 = f.region_min_y if y0 is None else y0
+        w = f.xres if w is None else w
+        h = f.yres if h is None else h
         if out is None:
-            out = np.zeros((f.yres, f.xres, 4), np.float32)
-        _check(lib().lb_imager_resolve_host(self._h, aov, f.region_min_x, f.region_min_y, f.xres, f.yres, _hptr(out)))
+            out = np.zeros((h, w, 4), np.float32)
+        _check(lib().lb_imager_resolve_host(self._h, aov, x0, y0, w, h, _hptr(out)))
         return out
 
     def buffers(self, aov: int):
@@ -303,12 +319,35 @@ class Camera:
 
     def comm_init(self, world_size: int, rank: int, unique_id: bytes):
         _check(lib().lb_comm_init(self._h, world_size, rank, unique_id))
+        self._rank = rank
 
     def filter_set_sample_base(self, base: int):
         _check(lib().lb_filter_set_sample_base(self._h, base))
 
     def filter_reduce(self, root: int = -1, stream=None):
         _check(lib().lb_filter_reduce(self._h, root, _stream_ptr(stream)))
+
+    def filter_reduce_scatter(self, stream=None):
+        """Sum-reduce that leaves every rank owning one pixel slab of every plane (ncclReduceScatter per plane)."""
+        _check(lib().lb_filter_reduce_scatter(self._h, _stream_ptr(stream)))
+
+    def filter_slab(self):
+        """(first pixel, pixel count) of the slab this rank owns after filter_reduce_scatter."""
+        lo, n = C.c_size_t(), C.c_size_t()
+        _check(lib().lb_filter_slab(self._h, C.byref(lo), C.byref(n)))
+        return lo.value, n.value
+
+    def resolve_gather(self, aov: int, root: int = 0, stream=None, out=None):
+        """Every rank resolves its slab; the slabs are gathered on `root` (< 0: on every rank).  Returns the [yres, xres, 4]
+        device tensor on the ranks that receive the image, None elsewhere."""
+        import torch
+
+        f = self._frame
+        rank_gets = out is not None or root < 0 or self._rank == root
+        if out is None and rank_gets:
+            out = torch.empty((f.yres, f.xres, 4), dtype=torch.float32, device=f"cuda:{self.device}")
+        _check(lib().lb_imager_resolve_gather(self._h, aov, _dptr(out), root, _stream_ptr(stream)))
+        return out if rank_gets else None
 
     def comm_destroy(self):
         _check(lib().lb_comm_destroy(self._h))

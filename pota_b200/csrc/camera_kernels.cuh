@@ -78,7 +78,7 @@ LB_DEV void camera_create_ray(const E &ev, const CamConsts<float> &cam, const Ra
   const float sx = __ldg(io.sx + i), sy = __ldg(io.sy + i);
   const float dsx = __ldg(io.dsx + i), dsy = __ldg(io.dsy + i);
   float r1 = __ldg(io.lensx + i), r2 = __ldg(io.lensy + i);
-  const uint32_t ray_id = (uint32_t)(ray_id_base + i);
+  const uint32_t ray_id = ray_seed_word(ray_id_base + i);
   const float step = 0.001f;
   int tries = 0;
   // differential rays: baseline `step` of the reference, optionally stretched ("differentials")
@@ -250,7 +250,7 @@ LB_DEV void camera_create_ray_pair(const E &ev, const CamConsts<float> &cam, con
     sx[h] = __ldg(io.sx + k); sy[h] = __ldg(io.sy + k);
     dsx[h] = __ldg(io.dsx + k); dsy[h] = __ldg(io.dsy + k);
     r1[h] = __ldg(io.lensx + k); r2[h] = __ldg(io.lensy + k);
-    ray_id[h] = (uint32_t)(ray_id_base + k);
+    ray_id[h] = ray_seed_word(ray_id_base + k);
   }
   const float step = 0.001f;
   const float fd = step * cam.deriv_baseline;

@@ -41,6 +41,9 @@ __device__ void crypto_build_cache(const AovSet &aovs, const SampleIO &s, int a,
   auto add = [&](float k, float v) {
     for (int j = 0; j < m; ++j)
       if (key[j] == k) { wgt[j] += v; return; }
+    // at most D distinct ids exist; an id that never compares equal to itself (NaN: Cryptomatte never emits one) could
+    // otherwise claim a ninth entry through the trailing quota
+    if (m == kCryptoMaxDepth) return;
     key[m] = k; wgt[m] = 0.0f + v; ++m;
   };
   float iterative_transparency_weight = 1.0f, quota = 1.0f, sample_value = 0.0f;
@@ -63,7 +66,12 @@ __global__ void __launch_bounds__(256)
 k_filter_classify(const __grid_constant__ FilterConsts fc, const __grid_constant__ AovSet aovs, const __grid_constant__ SampleIO s,
                   WorkItem *__restrict__ work, FilterCounters *__restrict__ counters, uint64_t sample_base) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool active = i < s.n;
+  bool active = i < s.n;
+  if (active) {  // samples filtered for a pixel outside the region cannot be accumulated anywhere: dropped (the arrays come
+                 // from an external host; the reference would index out of bounds, lentil.h:941)
+    const int px = __ldg(s.px + i), py = __ldg(s.py + i);
+    if (px < 0 || py < 0 || px >= fc.xres || py >= fc.yres) active = false;
+  }
   bool redistribute = active;
   int samples = 0;
   float add_energy = 0.f;
@@ -85,6 +93,12 @@ k_filter_classify(const __grid_constant__ FilterConsts fc, const __grid_constant
     if ((depth == 1.0e30f || small) && !fc.enable_skydome) redistribute = false;
     const uint32_t flags = s.flags ? __ldg(s.flags + i) : 0u;
     if (flags & 1u) redistribute = false;  // volume_in_sample (:135-137)
+    {  // AiM4PointByMatrixMult(world_to_camera_matrix, sample_pos_ws) (:141-142); identity unless the batch carries a matrix
+      const float x = csp[0], y = csp[1], z = csp[2];
+      csp[0] = x * s.w2c[0][0] + y * s.w2c[1][0] + z * s.w2c[2][0] + s.w2c[3][0];
+      csp[1] = x * s.w2c[0][1] + y * s.w2c[1][1] + z * s.w2c[2][1] + s.w2c[3][1];
+      csp[2] = x * s.w2c[0][2] + y * s.w2c[1][2] + z * s.w2c[2][2] + s.w2c[3][2];
+    }
     csp[0] *= fc.unit_mult; csp[1] *= fc.unit_mult; csp[2] *= fc.unit_mult;  // :143-148
     if (s.transmission) {  // :152-159
       const float4 t = __ldg(s.transmission + i);

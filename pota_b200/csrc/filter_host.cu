@@ -35,9 +35,18 @@ struct FilterState {
   int n_aov = 0;
   lb_aov_desc aovs[kMaxAov]{};
   size_t npx = 0;
-  float *block = nullptr;  // [n_aov][npx] float4 planes, then [npx] weight: one contiguous reduction unit
+  size_t npx_pad = 0;      // plane stride in pixels: npx rounded up to kSlabAlign so that every world size that divides
+                           // kSlabAlign owns an equal, contiguous pixel slab of each plane (lb_filter_reduce_scatter)
+  float *block = nullptr;  // [n_aov][npx_pad] float4 planes, then [npx_pad] weight: one contiguous reduction unit
   size_t block_floats = 0;
   unsigned long long *zkey = nullptr, *zkey_debug = nullptr;
+  size_t zkey_npx = 0;     // pixels the two key planes are allocated for
+  // Every operation that touches the framebuffers waits for `ev_done` on its stream and records it again when it
+  // has issued its work: accumulates, reduces and resolves issued on DIFFERENT streams execute in call order (they
+  // share the work list, the counters and the planes).
+  cudaEvent_t ev_done = nullptr;
+  bool scattered = false;  // lb_filter_reduce_scatter has run: this rank's planes are complete only inside its slab
+  float4 *gather = nullptr;  // [npx_pad] resolved pixels of one AOV (lb_imager_resolve_gather)
   bool has_closest = false, has_debug_closest = false;
   WorkItem *work = nullptr;
   size_t work_cap = 0;
@@ -53,10 +62,18 @@ struct FilterState {
   FilterCounters *d_counters = nullptr;
   uint64_t sample_base = 0;
   uint64_t samples_seen = 0;  // source samples handed to accumulate since lb_filter_begin
-  // host-path staging
-  char *stage = nullptr;
+  // host-path staging: two device blocks so that the copy of chunk k+1 overlaps the kernels of chunk k
+  char *stage[2] = {nullptr, nullptr};
   size_t stage_bytes = 0;
-  cudaStream_t stream = nullptr;
+  cudaEvent_t stage_ready[2] = {nullptr, nullptr}, stage_free[2] = {nullptr, nullptr};
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  // lb_imager_resolve_host: the whole region of an AOV is resolved once into pinned host memory, buckets are served from it
+  float4 *res_dev = nullptr;           // [npx]
+  uint8_t *brk_dev = nullptr;          // [npx] cryptomatte: pixel holds <= rank ids (ends a bucket row, lentil_imager.cpp:132-134)
+  float4 *res_host[kMaxAov] = {};      // pinned, [npx] each, allocated on first use
+  uint8_t *brk_host[kMaxAov] = {};
+  bool res_valid[kMaxAov] = {};
+  size_t res_npx = 0;
   // NCCL
   ncclComm_t comm = nullptr;
   int world = 1, rank = 0;
@@ -64,6 +81,9 @@ struct FilterState {
 namespace lb { FilterState *&cam_filter(lb_camera *c); }
 
 namespace {
+
+// plane stride granule in pixels: 5040 = 2^4 * 3^2 * 5 * 7, so 1..10, 12, 14, 15, 16 ranks own equal contiguous slabs
+constexpr size_t kSlabAlign = 5040;
 
 struct DeviceGuard {
   int prev = -1;
@@ -89,6 +109,10 @@ struct NcclApi {
   decltype(&ncclAllReduce) AllReduce = nullptr;
   decltype(&ncclReduce) Reduce = nullptr;
   decltype(&ncclBroadcast) Broadcast = nullptr;
+  decltype(&ncclReduceScatter) ReduceScatter = nullptr;
+  decltype(&ncclAllGather) AllGather = nullptr;
+  decltype(&ncclSend) Send = nullptr;
+  decltype(&ncclRecv) Recv = nullptr;
   decltype(&ncclGroupStart) GroupStart = nullptr;
   decltype(&ncclGroupEnd) GroupEnd = nullptr;
   decltype(&ncclGetErrorString) GetErrorString = nullptr;
@@ -105,7 +129,7 @@ NcclApi *load_nccl() {
     }
     if (!api.h) return;
 #define SYM(f) api.f = (decltype(api.f))dlsym(api.h, "nccl" #f)
-    SYM(GetUniqueId); SYM(CommInitRank); SYM(CommDestroy); SYM(AllReduce); SYM(Reduce); SYM(Broadcast); SYM(GroupStart); SYM(GroupEnd); SYM(GetErrorString);
+    SYM(GetUniqueId); SYM(CommInitRank); SYM(CommDestroy); SYM(AllReduce); SYM(Reduce); SYM(Broadcast); SYM(ReduceScatter); SYM(AllGather); SYM(Send); SYM(Recv); SYM(GroupStart); SYM(GroupEnd); SYM(GetErrorString);
 #undef SYM
   });
   return (api.h && api.GetUniqueId && api.CommInitRank && api.AllReduce && api.Reduce) ? &api : nullptr;
@@ -146,7 +170,7 @@ void fill_aovs(const FilterState *f, AovSet &A, const lb_samples *S) {
   A.crypto_slots = f->crypto_slots;
   A.crypto_depth = S ? S->crypto_depth : 0;
   for (int a = 0; a < f->n_aov; ++a) {
-    A.buffer[a] = (float4 *)(f->block + (size_t)a * f->npx * 4);
+    A.buffer[a] = (float4 *)(f->block + (size_t)a * f->npx_pad * 4);
     A.values[a] = values ? (const float4 *)values[a] : nullptr;
     A.filter[a] = f->aovs[a].filter;
     A.role[a] = f->aovs[a].role;
@@ -159,7 +183,7 @@ void fill_aovs(const FilterState *f, AovSet &A, const lb_samples *S) {
       A.crypto_cache[a] = f->crypto_cache ? f->crypto_cache + (size_t)t * f->work_cap * f->crypto_cache_stride : nullptr;
     }
   }
-  A.weight = f->block + (size_t)f->n_aov * f->npx * 4;
+  A.weight = f->block + (size_t)f->n_aov * f->npx_pad * 4;
   A.zkey = f->zkey;
   A.zkey_debug = f->zkey_debug;
   A.debug_samples = f->has_debug_closest ? f->debug_samples : nullptr;
@@ -193,6 +217,12 @@ int accumulate_device(lb_camera *c, FilterState *f, const lb_samples *S, cudaStr
   SampleIO io{S->n, S->px, S->py, (const float4 *)S->rgba, (const float4 *)S->pos_cs, (const float4 *)S->raydir,
               (const float4 *)S->transmission, S->flags, S->inv_density,
               f->n_crypto && S->crypto_depth > 0 ? S->crypto_count : nullptr, f->n_crypto && S->crypto_depth > 0 ? S->crypto_opacity : nullptr};
+  // AiWorldToCameraMatrix of the batch (lentil_filter.cpp:139-142); identity when the caller hands camera-space positions
+  for (int r = 0; r < 4; ++r)
+    for (int k = 0; k < 3; ++k) io.w2c[r][k] = S->world_to_camera ? S->world_to_camera[4 * r + k] : (r == k ? 1.0f : 0.0f);
+  CUF(cudaStreamWaitEvent(stream, f->ev_done, 0));  // the batch scratch and the planes are shared with the previous call
+  f->scattered = false;
+  for (int a = 0; a < f->n_aov; ++a) f->res_valid[a] = false;
   CUF(cudaMemsetAsync(&f->d_counters->work_count, 0, 2 * sizeof(unsigned), stream));
   CUF(launch_filter_classify(fc, A, io, f->work, f->d_counters, f->sample_base, stream));
   if (cam_params(c).camera_type == LB_CAMERA_THINLENS)
@@ -201,6 +231,7 @@ int accumulate_device(lb_camera *c, FilterState *f, const lb_samples *S, cudaStr
     CUF(launch_filter_splat(cam_lens_kernel(c), cam_lens(c), cam_consts(c), fc, A, io, f->work, f->d_counters, f->sample_base,
                             cam_num_sms(c), stream));
   if (f->has_closest || f->has_debug_closest) CUF(launch_closest_gather(fc, A, io, f->sample_base, stream));
+  CUF(cudaEventRecord(f->ev_done, stream));
   f->sample_base += S->n;
   f->samples_seen += S->n;
   return LB_OK;
@@ -220,8 +251,15 @@ void filter_state_destroy(FilterState *f) {
   if (f->comm) { if (NcclApi *n = load_nccl()) n->CommDestroy(f->comm); }
   cudaFree(f->block); cudaFree(f->zkey); cudaFree(f->zkey_debug); cudaFree(f->work); cudaFree(f->debug_samples);
   cudaFree(f->crypto_tables); cudaFree(f->crypto_cache);
-  cudaFree(f->d_counters); cudaFree(f->stage);
+  cudaFree(f->d_counters); cudaFree(f->stage[0]); cudaFree(f->stage[1]); cudaFree(f->gather); cudaFree(f->res_dev); cudaFree(f->brk_dev);
+  for (int a = 0; a < kMaxAov; ++a) { cudaFreeHost(f->res_host[a]); cudaFreeHost(f->brk_host[a]); }
+  for (int i = 0; i < 2; ++i) {
+    if (f->stage_ready[i]) cudaEventDestroy(f->stage_ready[i]);
+    if (f->stage_free[i]) cudaEventDestroy(f->stage_free[i]);
+  }
+  if (f->ev_done) cudaEventDestroy(f->ev_done);
   if (f->stream) cudaStreamDestroy(f->stream);
+  if (f->copy_stream) cudaStreamDestroy(f->copy_stream);
   delete f;
 }
 
@@ -235,20 +273,34 @@ int lb_filter_begin(lb_camera *c, const lb_frame_desc *frame, int n_aov, const l
   FilterState *&slot = cam_filter(c);
   FilterState *f = slot;
   if (!f) { f = new FilterState(); slot = f; }
+  if (!f->stream) CUF(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking));
+  if (!f->copy_stream) CUF(cudaStreamCreateWithFlags(&f->copy_stream, cudaStreamNonBlocking));
+  if (!f->ev_done) {
+    CUF(cudaEventCreateWithFlags(&f->ev_done, cudaEventDisableTiming));
+    CUF(cudaEventRecord(f->ev_done, f->stream));
+  }
   f->frame = *frame;
   f->n_aov = n_aov;
   memcpy(f->aovs, aovs, n_aov * sizeof(lb_aov_desc));
   const size_t npx = (size_t)frame->xres * frame->yres;
-  const size_t floats = npx * (4 * (size_t)n_aov + 1);
-  if (floats != f->block_floats) {  // destroy_buffers + reallocate (lentil.h:214,1096-1117)
-    cudaFree(f->block); cudaFree(f->zkey); cudaFree(f->zkey_debug);
-    f->block = nullptr; f->zkey = f->zkey_debug = nullptr;
+  const size_t npx_pad = (npx + kSlabAlign - 1) / kSlabAlign * kSlabAlign;
+  const size_t floats = npx_pad * (4 * (size_t)n_aov + 1);
+  // destroy_buffers + reallocate (lentil.h:214,1096-1117).  cudaFree waits for work in flight on the old buffers.
+  if (floats != f->block_floats) {
+    cudaFree(f->block);
+    f->block = nullptr; f->block_floats = 0;
     CUF(cudaMalloc(&f->block, floats * sizeof(float)));
-    CUF(cudaMalloc(&f->zkey, npx * sizeof(unsigned long long)));
-    CUF(cudaMalloc(&f->zkey_debug, npx * sizeof(unsigned long long)));
     f->block_floats = floats;
   }
+  if (npx != f->zkey_npx) {  // sized by the pixel count alone: two frames can share `floats` and differ in npx
+    cudaFree(f->zkey); cudaFree(f->zkey_debug); cudaFree(f->gather);
+    f->zkey = f->zkey_debug = nullptr; f->gather = nullptr; f->zkey_npx = 0;
+    CUF(cudaMalloc(&f->zkey, npx * sizeof(unsigned long long)));
+    CUF(cudaMalloc(&f->zkey_debug, npx * sizeof(unsigned long long)));
+    f->zkey_npx = npx;
+  }
   f->npx = npx;
+  f->npx_pad = npx_pad;
   // cryptomatte tables (AOVData::allocate_cryptomatte_buffers, aov_data.h:145-150)
   int n_crypto = 0;
   for (int a = 0; a < n_aov; ++a) {
@@ -270,27 +322,34 @@ int lb_filter_begin(lb_camera *c, const lb_frame_desc *frame, int n_aov, const l
   if (n_crypto != f->n_crypto || table_words != f->crypto_table_words) {
     cudaFree(f->crypto_tables); cudaFree(f->crypto_cache);
     f->crypto_tables = nullptr; f->crypto_cache = nullptr; f->crypto_cache_stride = 0;
+    f->n_crypto = 0; f->crypto_table_words = 0;
     if (n_crypto) CUF(cudaMalloc(&f->crypto_tables, (size_t)n_crypto * table_words * 4));
     f->n_crypto = n_crypto;
     f->crypto_table_words = table_words;
   }
   f->crypto_slots = n_crypto ? slots : 0;
+  if (!f->d_counters) CUF(cudaMalloc(&f->d_counters, sizeof(FilterCounters)));
+  // zero everything on the filter's stream, ordered after whatever still reads the previous frame; the first
+  // accumulate waits for `ev_done` on its own stream
+  cudaStream_t st = f->stream;
+  CUF(cudaStreamWaitEvent(st, f->ev_done, 0));
   for (int t = 0; t < n_crypto; ++t) {
     uint32_t *tab = f->crypto_tables + (size_t)t * table_words;
-    CUF(cudaMemset(tab, 0xFF, table_words / 2 * 4));               // ids: kCryptoFree
-    CUF(cudaMemset(tab + table_words / 2, 0, table_words / 2 * 4)); // weights
+    CUF(cudaMemsetAsync(tab, 0xFF, table_words / 2 * 4, st));               // ids: kCryptoFree
+    CUF(cudaMemsetAsync(tab + table_words / 2, 0, table_words / 2 * 4, st)); // weights
   }
   f->has_closest = f->has_debug_closest = false;
   for (int a = 0; a < n_aov; ++a)
     if (aovs[a].filter == LB_FILTER_CLOSEST) (aovs[a].role == LB_AOV_LENTIL_DEBUG ? f->has_debug_closest : f->has_closest) = true;
-  CUF(cudaMemset(f->block, 0, floats * sizeof(float)));
-  CUF(cudaMemset(f->zkey, 0xFF, npx * sizeof(unsigned long long)));
-  CUF(cudaMemset(f->zkey_debug, 0xFF, npx * sizeof(unsigned long long)));
-  if (!f->d_counters) CUF(cudaMalloc(&f->d_counters, sizeof(FilterCounters)));
-  CUF(cudaMemset(f->d_counters, 0, sizeof(FilterCounters)));
-  if (!f->stream) CUF(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking));
+  CUF(cudaMemsetAsync(f->block, 0, floats * sizeof(float), st));
+  if (f->has_closest) CUF(cudaMemsetAsync(f->zkey, 0xFF, npx * sizeof(unsigned long long), st));
+  if (f->has_debug_closest) CUF(cudaMemsetAsync(f->zkey_debug, 0xFF, npx * sizeof(unsigned long long), st));
+  CUF(cudaMemsetAsync(f->d_counters, 0, sizeof(FilterCounters), st));
+  CUF(cudaEventRecord(f->ev_done, st));
   f->sample_base = 0;
   f->samples_seen = 0;
+  f->scattered = false;
+  for (int a = 0; a < kMaxAov; ++a) f->res_valid[a] = false;
   return LB_OK;
 }
 
@@ -310,37 +369,49 @@ int lb_filter_accumulate(lb_camera *c, const lb_samples *S, lb_stream stream) {
   return accumulate_device(c, f, S, (cudaStream_t)stream);
 }
 
-// Host-buffer variant: samples are staged to the device in chunks on the filter's own stream.
+// Host-buffer variant: samples are staged to the device in chunks through TWO staging blocks: the copies of chunk k+1
+// (copy stream) overlap the classify / splat kernels of chunk k (filter stream).  Source memory may be pageable
+// (Arnold's sample buffers are): the driver then stages the copy itself, still beside the kernels.
 int lb_filter_accumulate_host(lb_camera *c, const lb_samples *S) {
   if (!c || !S) return lb_fail(LB_ERR_INVALID, "null argument");
   FilterState *f = cam_filter(c);
   if (!f) return lb_fail(LB_ERR_STATE, "lb_filter_begin has not been called");
   if (S->n && (!S->px || !S->py || !S->rgba || !S->pos_cs)) return lb_fail(LB_ERR_INVALID, "null sample array");
+  if (S->crypto_depth < 0 || S->crypto_depth > LB_CRYPTO_MAX_DEPTH) return lb_fail(LB_ERR_INVALID, "crypto_depth outside [0, LB_CRYPTO_MAX_DEPTH]");
+  if (S->n == 0) return LB_OK;
   std::lock_guard<std::mutex> lk(cam_mutex(c));
   DeviceGuard g(cam_device(c));
-  const size_t chunk = std::min<size_t>(std::max<size_t>(S->n, 1), (size_t)1 << 22);
+  const size_t chunk = std::min<size_t>(S->n, (size_t)1 << 21);
   int n_val = 0;
   for (int a = 0; a < f->n_aov; ++a) if (S->aov_values && S->aov_values[a]) ++n_val;
-  // per-sample bytes: px,py (8) + rgba,pos (32) + raydir,transmission (32) + flags (4) + values
-  if (S->crypto_depth < 0 || S->crypto_depth > LB_CRYPTO_MAX_DEPTH) return lb_fail(LB_ERR_INVALID, "crypto_depth outside [0, LB_CRYPTO_MAX_DEPTH]");
   const size_t Dn = f->n_crypto ? (size_t)S->crypto_depth : 0;
   int n_ids = 0;
   for (int a = 0; a < f->n_aov; ++a) if (Dn && S->crypto_ids && S->crypto_ids[a]) ++n_ids;
+  // per-sample bytes: px,py (8) + rgba,pos (32) + raydir,transmission (32) + flags (4) + values + cryptomatte sub-samples
   const size_t per = 8 + 32 + (S->raydir ? 16 : 0) + (S->transmission ? 16 : 0) + (S->flags ? 4 : 0) + 16 * (size_t)n_val +
                      (Dn ? 1 + 4 * Dn * (1 + (size_t)n_ids) : 0);
   const size_t need = per * chunk + 256 * (16 + 2 * kMaxAov);
   if (f->stage_bytes < need) {
-    cudaFree(f->stage); f->stage = nullptr; f->stage_bytes = 0;
-    CUF(cudaMalloc(&f->stage, need));
+    for (int i = 0; i < 2; ++i) {
+      cudaFree(f->stage[i]); f->stage[i] = nullptr;
+      if (!f->stage_ready[i]) CUF(cudaEventCreateWithFlags(&f->stage_ready[i], cudaEventDisableTiming));
+      if (!f->stage_free[i]) CUF(cudaEventCreateWithFlags(&f->stage_free[i], cudaEventDisableTiming));
+    }
+    f->stage_bytes = 0;
+    for (int i = 0; i < 2; ++i) CUF(cudaMalloc(&f->stage[i], need));
     f->stage_bytes = need;
   }
-  for (size_t base = 0; base < S->n; base += chunk) {
+  int rc = LB_OK;
+  size_t k = 0;
+  for (size_t base = 0; base < S->n && rc == LB_OK; base += chunk, ++k) {
+    const int slot = (int)(k & 1);
     const size_t m = std::min(chunk, S->n - base);
-    char *p = f->stage;
+    if (k >= 2) CUF(cudaStreamWaitEvent(f->copy_stream, f->stage_free[slot], 0));  // the kernels of chunk k-2 have read this block
+    char *p = f->stage[slot];
     auto put = [&](const void *src, size_t elem) -> void * {
       if (!src) return nullptr;
       void *d = p;
-      cudaMemcpyAsync(d, (const char *)src + base * elem, m * elem, cudaMemcpyHostToDevice, f->stream);
+      cudaMemcpyAsync(d, (const char *)src + base * elem, m * elem, cudaMemcpyHostToDevice, f->copy_stream);
       p += (chunk * elem + 255) & ~(size_t)255;
       return d;
     };
@@ -364,11 +435,13 @@ int lb_filter_accumulate_host(lb_camera *c, const lb_samples *S) {
       D.crypto_count = (const uint8_t *)put(S->crypto_count, 1);
     }
     CUF(cudaGetLastError());
-    int rc = accumulate_device(c, f, &D, f->stream);
-    if (rc != LB_OK) return rc;
-    CUF(cudaStreamSynchronize(f->stream));  // the staging block is reused by the next chunk
+    CUF(cudaEventRecord(f->stage_ready[slot], f->copy_stream));
+    CUF(cudaStreamWaitEvent(f->stream, f->stage_ready[slot], 0));
+    rc = accumulate_device(c, f, &D, f->stream);
+    CUF(cudaEventRecord(f->stage_free[slot], f->stream));
   }
-  return LB_OK;
+  CUF(cudaStreamSynchronize(f->stream));  // the caller may reuse its arrays and the result is complete on return
+  return rc;
 }
 
 int lb_filter_get_stats(lb_camera *c, lb_filter_stats *out) {
@@ -396,53 +469,99 @@ int lb_filter_newton_iterations(lb_camera *c, uint64_t *out) {  // diagnostic: l
   return LB_OK;
 }
 
-int lb_imager_resolve(lb_camera *c, int aov, int x0, int y0, int w, int h, float *rgba_out, lb_stream stream) {
+int lb_imager_resolve(lb_camera *c, int aov, int x0, int y0, int w, int h, float *rgba_out, lb_stream stream_) {
   if (!c || !rgba_out) return lb_fail(LB_ERR_INVALID, "null argument");
   FilterState *f = cam_filter(c);
   if (!f) return lb_fail(LB_ERR_STATE, "lb_filter_begin has not been called");
   if (aov < 0 || aov >= f->n_aov) return lb_fail(LB_ERR_INVALID, "aov index out of range");
   const int rx = x0 - f->frame.region_min_x, ry = y0 - f->frame.region_min_y;
   if (rx < 0 || ry < 0 || w < 0 || h < 0 || rx + w > f->frame.xres || ry + h > f->frame.yres) return lb_fail(LB_ERR_INVALID, "bucket outside the region");
+  if (f->scattered) return lb_fail(LB_ERR_STATE, "after lb_filter_reduce_scatter a rank holds only its slab: use lb_imager_resolve_gather");
   DeviceGuard g(cam_device(c));
+  cudaStream_t stream = (cudaStream_t)stream_;
+  CUF(cudaStreamWaitEvent(stream, f->ev_done, 0));
   if (f->crypto_of[aov] >= 0) {
     const uint32_t *key = f->crypto_tables + (size_t)f->crypto_of[aov] * f->crypto_table_words;
-    CUF(launch_resolve_crypto(key, (const float *)(key + f->crypto_table_words / 2), (const float4 *)(f->block + (size_t)aov * f->npx * 4),
-                              f->crypto_slots, f->crypto_rank[aov], f->frame.xres, rx, ry, w, h, (float4 *)rgba_out, (cudaStream_t)stream));
-    return LB_OK;
+    CUF(launch_resolve_crypto(key, (const float *)(key + f->crypto_table_words / 2), (const float4 *)(f->block + (size_t)aov * f->npx_pad * 4),
+                              f->crypto_slots, f->crypto_rank[aov], f->frame.xres, rx, ry, w, h, (float4 *)rgba_out, nullptr, stream));
+  } else {
+    CUF(launch_resolve((const float4 *)(f->block + (size_t)aov * f->npx_pad * 4), f->block + (size_t)f->n_aov * f->npx_pad * 4, f->aovs[aov].filter,
+                       f->aovs[aov].role, f->frame.xres, rx, ry, w, h, (float4 *)rgba_out, stream));
   }
-  CUF(launch_resolve((const float4 *)(f->block + (size_t)aov * f->npx * 4), f->block + (size_t)f->n_aov * f->npx * 4, f->aovs[aov].filter,
-                     f->aovs[aov].role, f->frame.xres, rx, ry, w, h, (float4 *)rgba_out, (cudaStream_t)stream));
+  CUF(cudaEventRecord(f->ev_done, stream));
   return LB_OK;
 }
 
+// driver_process_bucket with a HOST bucket.  Arnold calls it once per bucket and output (8 100 buckets of 16 x 16 pixels
+// at 1080p): the first call after the frame changed resolves the WHOLE region of that AOV on the device into pinned
+// host memory (one kernel, one copy), every call then copies its bucket rows out of that image on the host.
+// Cryptomatte rows end at the first pixel of the BUCKET row holding <= rank ids (lentil_imager.cpp:132-134), which
+// depends on the bucket: the device marks those pixels and the row copy stops at the first mark.
 int lb_imager_resolve_host(lb_camera *c, int aov, int x0, int y0, int w, int h, float *rgba_out) {
   if (!c || !rgba_out) return lb_fail(LB_ERR_INVALID, "null argument");
   FilterState *f = cam_filter(c);
   if (!f) return lb_fail(LB_ERR_STATE, "lb_filter_begin has not been called");
-  DeviceGuard g(cam_device(c));
-  float *d = nullptr;
-  const size_t bytes = (size_t)std::max(w, 0) * std::max(h, 0) * 16;
-  if (bytes == 0) return LB_OK;
-  CUF(cudaMalloc(&d, bytes));
-  CUF(cudaDeviceSynchronize());  // accumulates may still be running on the caller's streams
-  if (aov >= 0 && aov < f->n_aov && f->crypto_of[aov] >= 0)  // cryptomatte rows can end early and keep the bucket's contents
-    CUF(cudaMemcpyAsync(d, rgba_out, bytes, cudaMemcpyHostToDevice, f->stream));
-  int rc = lb_imager_resolve(c, aov, x0, y0, w, h, d, f->stream);
-  if (rc == LB_OK) {
-    cudaError_t e = cudaMemcpyAsync(rgba_out, d, bytes, cudaMemcpyDeviceToHost, f->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(f->stream);
-    if (e != cudaSuccess) rc = lb_fail(LB_ERR_CUDA, cudaGetErrorString(e));
+  if (aov < 0 || aov >= f->n_aov) return lb_fail(LB_ERR_INVALID, "aov index out of range");
+  const int rx = x0 - f->frame.region_min_x, ry = y0 - f->frame.region_min_y;
+  if (rx < 0 || ry < 0 || w < 0 || h < 0 || rx + w > f->frame.xres || ry + h > f->frame.yres) return lb_fail(LB_ERR_INVALID, "bucket outside the region");
+  if (w == 0 || h == 0) return LB_OK;
+  if (f->scattered) return lb_fail(LB_ERR_STATE, "after lb_filter_reduce_scatter a rank holds only its slab: use lb_imager_resolve_gather");
+  std::lock_guard<std::mutex> lk(cam_mutex(c));
+  const bool crypto = f->crypto_of[aov] >= 0;
+  if (!f->res_valid[aov] || f->res_npx != f->npx) {
+    DeviceGuard g(cam_device(c));
+    if (f->res_npx != f->npx) {
+      cudaFree(f->res_dev); cudaFree(f->brk_dev);
+      f->res_dev = nullptr; f->brk_dev = nullptr;
+      for (int a = 0; a < kMaxAov; ++a) {
+        cudaFreeHost(f->res_host[a]); cudaFreeHost(f->brk_host[a]);
+        f->res_host[a] = nullptr; f->brk_host[a] = nullptr; f->res_valid[a] = false;
+      }
+      f->res_npx = 0;
+      CUF(cudaMalloc(&f->res_dev, f->npx * sizeof(float4)));
+      CUF(cudaMalloc(&f->brk_dev, f->npx));
+      f->res_npx = f->npx;
+    }
+    if (!f->res_host[aov]) CUF(cudaMallocHost(&f->res_host[aov], f->npx * sizeof(float4)));
+    if (crypto && !f->brk_host[aov]) CUF(cudaMallocHost(&f->brk_host[aov], f->npx));
+    cudaStream_t st = f->stream;
+    CUF(cudaStreamWaitEvent(st, f->ev_done, 0));
+    const int xr = f->frame.xres, yr = f->frame.yres;
+    if (crypto) {
+      const uint32_t *key = f->crypto_tables + (size_t)f->crypto_of[aov] * f->crypto_table_words;
+      CUF(cudaMemsetAsync(f->res_dev, 0, f->npx * sizeof(float4), st));
+      CUF(launch_resolve_crypto(key, (const float *)(key + f->crypto_table_words / 2), (const float4 *)(f->block + (size_t)aov * f->npx_pad * 4),
+                                f->crypto_slots, f->crypto_rank[aov], xr, 0, 0, xr, yr, f->res_dev, f->brk_dev, st));
+      CUF(cudaMemcpyAsync(f->brk_host[aov], f->brk_dev, f->npx, cudaMemcpyDeviceToHost, st));
+    } else {
+      CUF(launch_resolve((const float4 *)(f->block + (size_t)aov * f->npx_pad * 4), f->block + (size_t)f->n_aov * f->npx_pad * 4, f->aovs[aov].filter,
+                         f->aovs[aov].role, xr, 0, 0, xr, yr, f->res_dev, st));
+    }
+    CUF(cudaMemcpyAsync(f->res_host[aov], f->res_dev, f->npx * sizeof(float4), cudaMemcpyDeviceToHost, st));
+    CUF(cudaEventRecord(f->ev_done, st));
+    CUF(cudaStreamSynchronize(st));
+    f->res_valid[aov] = true;
   }
-  cudaFree(d);
-  return rc;
+  const float4 *img = f->res_host[aov];
+  const int xr = f->frame.xres;
+  for (int j = 0; j < h; ++j) {
+    const size_t row = (size_t)(ry + j) * xr + rx;
+    int n = w;
+    if (crypto) {
+      const uint8_t *b = f->brk_host[aov] + row;
+      for (n = 0; n < w && !b[n]; ++n) {}
+    }
+    memcpy(rgba_out + (size_t)j * w * 4, img + row, (size_t)n * sizeof(float4));
+  }
+  return LB_OK;
 }
 
 int lb_filter_buffers(lb_camera *c, int aov, float **buffer, float **weight) {
   FilterState *f = c ? cam_filter(c) : nullptr;
   if (!f) return lb_fail(LB_ERR_STATE, "lb_filter_begin has not been called");
   if (aov < 0 || aov >= f->n_aov) return lb_fail(LB_ERR_INVALID, "aov index out of range");
-  if (buffer) *buffer = f->block + (size_t)aov * f->npx * 4;
-  if (weight) *weight = f->block + (size_t)f->n_aov * f->npx * 4;
+  if (buffer) *buffer = f->block + (size_t)aov * f->npx_pad * 4;
+  if (weight) *weight = f->block + (size_t)f->n_aov * f->npx_pad * 4;
   return LB_OK;
 }
 
@@ -452,8 +571,8 @@ int lb_filter_buffers_host(lb_camera *c, int aov, float *buffer_out, float *weig
   if (aov < 0 || aov >= f->n_aov) return lb_fail(LB_ERR_INVALID, "aov index out of range");
   DeviceGuard g(cam_device(c));
   CUF(cudaDeviceSynchronize());
-  if (buffer_out) CUF(cudaMemcpy(buffer_out, f->block + (size_t)aov * f->npx * 4, f->npx * 16, cudaMemcpyDeviceToHost));
-  if (weight_out) CUF(cudaMemcpy(weight_out, f->block + (size_t)f->n_aov * f->npx * 4, f->npx * 4, cudaMemcpyDeviceToHost));
+  if (buffer_out) CUF(cudaMemcpy(buffer_out, f->block + (size_t)aov * f->npx_pad * 4, f->npx * 16, cudaMemcpyDeviceToHost));
+  if (weight_out) CUF(cudaMemcpy(weight_out, f->block + (size_t)f->n_aov * f->npx_pad * 4, f->npx * 4, cudaMemcpyDeviceToHost));
   return LB_OK;
 }
 
@@ -497,17 +616,16 @@ int lb_comm_init(lb_camera *c, int world_size, int rank, const uint8_t id_in[128
   return LB_OK;
 }
 
-int lb_filter_reduce(lb_camera *c, int root, lb_stream stream_) {
-  FilterState *f = c ? cam_filter(c) : nullptr;
-  if (!f) return lb_fail(LB_ERR_STATE, "lb_filter_begin has not been called");
-  if (f->world <= 1 || !f->comm) return LB_OK;  // single rank: nothing to combine
-  NcclApi *n = load_nccl();
-  if (!n) return lb_fail(LB_ERR_COMM, "NCCL unavailable");
-  DeviceGuard g(cam_device(c));
-  cudaStream_t stream = (cudaStream_t)stream_;
+}  // extern "C"
+
+namespace {
+// closest AOVs and cryptomatte tables: the parts of the combine that are not an element-wise sum.
+// Closest: global min of the depth keys, then every rank but the winner clears its pixel (so the sum keeps the winner's
+// value).  Cryptomatte: every rank's id tables are broadcast in turn and folded into the receivers' own (ids differ per
+// rank, so this is a merge, not an element-wise reduction); crypto_total_weight rides in the AOV plane and is summed.
+int reduce_keys_and_tables(FilterState *f, NcclApi *n, int root, cudaStream_t stream) {
   auto check = [&](ncclResult_t r) { return r == ncclSuccess ? LB_OK : lb_fail(LB_ERR_COMM, n->GetErrorString ? n->GetErrorString(r) : "nccl error"); };
   int rc;
-  // closest AOVs: global min of the depth keys, then every rank but the winner clears its pixel
   for (int pass = 0; pass < 2; ++pass) {
     const bool on = pass == 0 ? f->has_closest : f->has_debug_closest;
     if (!on) continue;
@@ -518,14 +636,11 @@ int lb_filter_reduce(lb_camera *c, int root, lb_stream stream_) {
     for (int a = 0; a < f->n_aov; ++a) {
       const bool dbg = f->aovs[a].role == LB_AOV_LENTIL_DEBUG;
       if (f->aovs[a].filter != LB_FILTER_CLOSEST || dbg != (pass == 1)) continue;
-      k_mask_closest<<<(unsigned)((f->npx + 255) / 256), 256, 0, stream>>>(local, global, (float4 *)(f->block + (size_t)a * f->npx * 4), f->npx);
+      k_mask_closest<<<(unsigned)((f->npx + 255) / 256), 256, 0, stream>>>(local, global, (float4 *)(f->block + (size_t)a * f->npx_pad * 4), f->npx);
     }
     CUF(cudaMemcpyAsync(local, global, f->npx * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, stream));
     CUF(cudaFreeAsync(global, stream));
   }
-  // cryptomatte tables: every rank's tables are broadcast in turn and folded into the receivers' own
-  // (ids differ per rank, so this is a merge, not an element-wise reduction).  crypto_total_weight rides in the
-  // AOV plane and is summed below.
   if (f->n_crypto) {
     if (!n->Broadcast) return lb_fail(LB_ERR_COMM, "ncclBroadcast unavailable");
     const size_t words = (size_t)f->n_crypto * f->crypto_table_words;
@@ -546,9 +661,123 @@ int lb_filter_reduce(lb_camera *c, int root, lb_stream stream_) {
     CUF(cudaFreeAsync(mine, stream));
     CUF(cudaFreeAsync(other, stream));
   }
+  return LB_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int lb_filter_reduce(lb_camera *c, int root, lb_stream stream_) {
+  FilterState *f = c ? cam_filter(c) : nullptr;
+  if (!f) return lb_fail(LB_ERR_STATE, "lb_filter_begin has not been called");
+  if (f->world <= 1 || !f->comm) return LB_OK;  // single rank: nothing to combine
+  NcclApi *n = load_nccl();
+  if (!n) return lb_fail(LB_ERR_COMM, "NCCL unavailable");
+  std::lock_guard<std::mutex> lk(cam_mutex(c));
+  DeviceGuard g(cam_device(c));
+  cudaStream_t stream = (cudaStream_t)stream_;
+  auto check = [&](ncclResult_t r) { return r == ncclSuccess ? LB_OK : lb_fail(LB_ERR_COMM, n->GetErrorString ? n->GetErrorString(r) : "nccl error"); };
+  CUF(cudaStreamWaitEvent(stream, f->ev_done, 0));
+  for (int a = 0; a < f->n_aov; ++a) f->res_valid[a] = false;
+  int rc = reduce_keys_and_tables(f, n, root, stream);
+  if (rc != LB_OK) return rc;
   // one sum-reduce over every AOV plane + the weight plane
   if (root < 0) rc = check(n->AllReduce(f->block, f->block, f->block_floats, ncclFloat32, ncclSum, f->comm, stream));
   else rc = check(n->Reduce(f->block, f->block, f->block_floats, ncclFloat32, ncclSum, root, f->comm, stream));
+  CUF(cudaEventRecord(f->ev_done, stream));
+  return rc;
+}
+
+// Sum-reduce where every rank ends up OWNING one pixel slab of every plane: per plane one in-place
+// ncclReduceScatter, all planes in one NCCL group.  Each rank then resolves its own slab and the resolved pixels are
+// gathered (lb_imager_resolve_gather): 1/world of the resolve work per rank and no root bottleneck in the reduction.
+int lb_filter_reduce_scatter(lb_camera *c, lb_stream stream_) {
+  FilterState *f = c ? cam_filter(c) : nullptr;
+  if (!f) return lb_fail(LB_ERR_STATE, "lb_filter_begin has not been called");
+  if (f->world <= 1 || !f->comm) return LB_OK;
+  NcclApi *n = load_nccl();
+  if (!n || !n->ReduceScatter) return lb_fail(LB_ERR_COMM, "NCCL unavailable");
+  if (f->npx_pad % (size_t)f->world) return lb_fail(LB_ERR_INVALID, "world size does not divide the plane granule (5040): use lb_filter_reduce");
+  if (f->n_crypto) return lb_fail(LB_ERR_INVALID, "frames with cryptomatte AOVs combine with lb_filter_reduce (the ranked resolve reads whole bucket rows)");
+  std::lock_guard<std::mutex> lk(cam_mutex(c));
+  DeviceGuard g(cam_device(c));
+  cudaStream_t stream = (cudaStream_t)stream_;
+  auto check = [&](ncclResult_t r) { return r == ncclSuccess ? LB_OK : lb_fail(LB_ERR_COMM, n->GetErrorString ? n->GetErrorString(r) : "nccl error"); };
+  CUF(cudaStreamWaitEvent(stream, f->ev_done, 0));
+  for (int a = 0; a < f->n_aov; ++a) f->res_valid[a] = false;
+  int rc = reduce_keys_and_tables(f, n, -1, stream);
+  if (rc != LB_OK) return rc;
+  const size_t slab = f->npx_pad / (size_t)f->world;  // pixels per rank
+  if ((rc = check(n->GroupStart())) != LB_OK) return rc;
+  for (int a = 0; a <= f->n_aov && rc == LB_OK; ++a) {
+    const size_t per_px = a < f->n_aov ? 4 : 1;  // float4 planes, then the float weight plane
+    float *plane = f->block + (size_t)a * f->npx_pad * 4;
+    rc = check(n->ReduceScatter(plane, plane + (size_t)f->rank * slab * per_px, slab * per_px, ncclFloat32, ncclSum, f->comm, stream));
+  }
+  const int rc2 = check(n->GroupEnd());
+  if (rc == LB_OK) rc = rc2;
+  f->scattered = rc == LB_OK;
+  CUF(cudaEventRecord(f->ev_done, stream));
+  return rc;
+}
+
+int lb_filter_slab(lb_camera *c, size_t *first_pixel, size_t *n_pixels) {
+  FilterState *f = c ? cam_filter(c) : nullptr;
+  if (!f) return lb_fail(LB_ERR_STATE, "lb_filter_begin has not been called");
+  const size_t slab = f->npx_pad / (size_t)std::max(f->world, 1);
+  const size_t lo = std::min((size_t)f->rank * slab, f->npx), hi = std::min(lo + slab, f->npx);
+  if (first_pixel) *first_pixel = lo;
+  if (n_pixels) *n_pixels = hi - lo;
+  return LB_OK;
+}
+
+// driver_process_bucket for the whole region after lb_filter_reduce_scatter: this rank resolves its slab, the slabs are
+// gathered on `root` (ncclSend / ncclRecv) or on every rank (root < 0, ncclAllGather).  rgba_out: [yres][xres][4] device
+// floats (only written where the result lands).
+int lb_imager_resolve_gather(lb_camera *c, int aov, float *rgba_out, int root, lb_stream stream_) {
+  FilterState *f = c ? cam_filter(c) : nullptr;
+  if (!f) return lb_fail(LB_ERR_STATE, "lb_filter_begin has not been called");
+  if (aov < 0 || aov >= f->n_aov) return lb_fail(LB_ERR_INVALID, "aov index out of range");
+  if (root >= f->world) return lb_fail(LB_ERR_INVALID, "root out of range");
+  std::lock_guard<std::mutex> lk(cam_mutex(c));
+  DeviceGuard g(cam_device(c));
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const bool single = f->world <= 1 || !f->comm;
+  if (!single && !f->scattered) return lb_fail(LB_ERR_STATE, "lb_filter_reduce_scatter has not been called for this frame");
+  const bool mine = single || root < 0 || root == f->rank;
+  if (mine && !rgba_out) return lb_fail(LB_ERR_INVALID, "null output on a receiving rank");
+  CUF(cudaStreamWaitEvent(stream, f->ev_done, 0));
+  const float4 *plane = (const float4 *)(f->block + (size_t)aov * f->npx_pad * 4);
+  const float *wplane = f->block + (size_t)f->n_aov * f->npx_pad * 4;
+  if (single) {
+    CUF(launch_resolve_linear(plane, wplane, f->aovs[aov].filter, f->aovs[aov].role, 0, f->npx, (float4 *)rgba_out, stream));
+    CUF(cudaEventRecord(f->ev_done, stream));
+    return LB_OK;
+  }
+  NcclApi *n = load_nccl();
+  if (!n || !n->AllGather || !n->Send || !n->Recv) return lb_fail(LB_ERR_COMM, "NCCL unavailable");
+  auto check = [&](ncclResult_t r) { return r == ncclSuccess ? LB_OK : lb_fail(LB_ERR_COMM, n->GetErrorString ? n->GetErrorString(r) : "nccl error"); };
+  if (!f->gather) CUF(cudaMalloc(&f->gather, f->npx_pad * sizeof(float4)));
+  const size_t slab = f->npx_pad / (size_t)f->world;
+  const size_t lo = (size_t)f->rank * slab;
+  const size_t cnt = lo < f->npx ? std::min(slab, f->npx - lo) : 0;
+  CUF(launch_resolve_linear(plane, wplane, f->aovs[aov].filter, f->aovs[aov].role, lo, cnt, f->gather + lo, stream));
+  int rc = LB_OK;
+  if (root < 0) {
+    rc = check(n->AllGather(f->gather + lo, f->gather, slab * 4, ncclFloat32, f->comm, stream));
+  } else {
+    if ((rc = check(n->GroupStart())) != LB_OK) return rc;
+    if (f->rank == root) {
+      for (int r = 0; r < f->world && rc == LB_OK; ++r)
+        if (r != root) rc = check(n->Recv(f->gather + (size_t)r * slab, slab * 4, ncclFloat32, r, f->comm, stream));
+    } else {
+      rc = check(n->Send(f->gather + lo, slab * 4, ncclFloat32, root, f->comm, stream));
+    }
+    const int rc2 = check(n->GroupEnd());
+    if (rc == LB_OK) rc = rc2;
+  }
+  if (rc == LB_OK && mine) CUF(cudaMemcpyAsync(rgba_out, f->gather, f->npx * sizeof(float4), cudaMemcpyDeviceToDevice, stream));
+  CUF(cudaEventRecord(f->ev_done, stream));
   return rc;
 }
 

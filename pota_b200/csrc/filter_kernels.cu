@@ -63,7 +63,7 @@ __global__ void k_resolve(const float4 *__restrict__ buffer, const float *__rest
 // order, which is what std::sort's insertion sort leaves for the map-ordered input of up to 16 entries.
 __global__ void __launch_bounds__(256)
 k_resolve_crypto(const uint32_t *__restrict__ key, const float *__restrict__ wgt, const float4 *__restrict__ total, int slots, int rank,
-                 int xres, int x0, int y0, int w, float4 *__restrict__ out) {
+                 int xres, int x0, int y0, int w, float4 *__restrict__ out, uint8_t *__restrict__ brk) {
   __shared__ int first_break;
   const int j = blockIdx.x;
   if (threadIdx.x == 0) first_break = w;
@@ -72,12 +72,14 @@ k_resolve_crypto(const uint32_t *__restrict__ key, const float *__restrict__ wgt
     const size_t p = (size_t)(y0 + j) * xres + (x0 + i);
     int size = 0;
     for (int k = 0; k < slots; ++k) size += key[p * slots + k] != kCryptoFree;
-    if (size <= rank) atomicMin(&first_break, i);
+    if (brk) brk[p] = size <= rank;
+    else if (size <= rank) atomicMin(&first_break, i);
   }
   __syncthreads();
   const int end = first_break;
   for (int i = threadIdx.x; i < end; i += blockDim.x) {
     const size_t p = (size_t)(y0 + j) * xres + (x0 + i);
+    if (brk && brk[p]) continue;
     const uint32_t *kp = key + p * slots;
     const float *wp = wgt + p * slots;
     const float tw = total[p].x;  // crypto_total_weight
@@ -109,9 +111,9 @@ k_crypto_merge(uint32_t *__restrict__ key, float *__restrict__ wgt, const uint32
 }
 
 cudaError_t launch_resolve_crypto(const uint32_t *key, const float *wgt, const float4 *total, int slots, int rank, int xres, int x0, int y0,
-                                  int w, int h, float4 *out, cudaStream_t stream) {
+                                  int w, int h, float4 *out, uint8_t *brk, cudaStream_t stream) {
   if (w <= 0 || h <= 0) return cudaSuccess;
-  k_resolve_crypto<<<h, 256, 0, stream>>>(key, wgt, total, slots, rank, xres, x0, y0, w, out);
+  k_resolve_crypto<<<h, 256, 0, stream>>>(key, wgt, total, slots, rank, xres, x0, y0, w, out, brk);
   return cudaGetLastError();
 }
 
@@ -138,6 +140,18 @@ cudaError_t launch_closest_gather(const FilterConsts &fc, const AovSet &aovs, co
                                   cudaStream_t stream) {
   const size_t npx = (size_t)fc.xres * fc.yres;
   k_closest_gather<<<(unsigned)((npx + 255) / 256), 256, 0, stream>>>(fc, aovs, s, sample_base);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_resolve_linear(const float4 *buffer, const float *weight, int filter, int role, size_t first, size_t count, float4 *out,
+                                  cudaStream_t stream) {
+  // a frame-wide row: k_resolve with xres = w = count chunks of at most 2^30 pixels
+  for (size_t done = 0; done < count;) {
+    const size_t m = count - done < ((size_t)1 << 30) ? count - done : ((size_t)1 << 30);
+    dim3 grid((unsigned)((m + 255) / 256), 1);
+    k_resolve<<<grid, 256, 0, stream>>>(buffer + first + done, weight + first + done, filter, role, (int)m, 0, 0, (int)m, 1, out + done);
+    done += m;
+  }
   return cudaGetLastError();
 }
 

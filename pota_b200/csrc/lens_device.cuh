@@ -23,6 +23,9 @@ LB_DEV uint32_t tea8(uint32_t v0, uint32_t v1) {  // tea<8>, global.h:32-46
   }
   return v0;
 }
+// 32-bit seed word of a 64-bit global ray index (retry RNG of the forward path): identical to the index below 2^32, the
+// high word is mixed in above it (8 GPUs x 5.3e8 rays per frame approach 2^32)
+LB_DEV uint32_t ray_seed_word(uint64_t id) { return (uint32_t)id ^ ((uint32_t)(id >> 32) * 0x9E3779B9u); }
 LB_DEV float lcg_rng(uint32_t &previous) {  // rng, global.h:51-57
   previous = previous * 1664525u + 1013904223u;
   return __uint2float_rn(previous & 0x00FFFFFFu) * (1.0f / 16777216.0f);  // exact: 24-bit / 2^24
@@ -367,11 +370,69 @@ LB_DEV void lt_iterate_tail(const C &cam, const T scene[3], T ax, T ay, const T 
   s.error = error;
   s.k += 1;
 }
+// sqrt for non-negative finite arguments on the special-function unit (MUFU.SQRT, 1-2 ulp); sqrtf is a MUFU.RSQ plus a
+// fix-up sequence with a slow-path branch
+LB_DEV float sqrt_approx(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// The same loop trip for the float kernels and a SPHERICAL outer pupil (every lens of the pack; warp-uniform test), with
+// sphereToCs (lens.h:99-125) and csToSphere (lens.h:127-153) fused: both build the same normal and tangent frame at the
+// outer-pupil point, the view vector need not be normalised before it is projected (one rsqrt of |view|^2 * |ex|^2
+// scales both projections), and each 2x2 Newton step applies the inverse determinant to the residual once instead of
+// to the four matrix entries.  Same mathematics as lt_iterate_tail, about 55 FP32 operations + 5 MUFU instead of ~130
+// (ncu r02: with the mirror-packed polynomials the tail had become 45 % of the instructions of a trip).
+template <typename C>
+LB_DEV void lt_iterate_tail_sphere(const C &cam, const float scene[3], float ax, float ay, const float ap[2], const float J[4], const float K[4],
+                                   LtState<float> &s) {
+  const float prev_sqr_err = s.sqr_err, prev_sqr_ap_err = s.sqr_ap_err;
+  const float da0 = ax - ap[0], da1 = ay - ap[1];
+  s.sqr_ap_err = da0 * da0 + da1 * da1;
+  const float ga = t_rcp(J[0] * J[3] - J[1] * J[2]);
+  const float a0 = da0 * ga, a1 = da1 * ga;
+  s.dx = fmaf(-J[1], a1, fmaf(J[3], a0, s.dx));
+  s.dy = fmaf(J[0], a1, fmaf(-J[2], a0, s.dy));
+  // outer-pupil point -> camera space (sphere centred at -R)
+  const float px = s.out[0], py = s.out[1];
+  const float r2 = px * px + py * py;
+  const float nx = px * cam.inv_outer_R, ny = py * cam.inv_outer_R;
+  const float nz = sqrt_approx(fmaxf(0.0f, cam.outer_R2 - r2)) * cam.abs_inv_outer_R;
+  const float pz = -fminf(r2, cam.outer_R2) * t_rcp(fmaf(cam.outer_R, nz, cam.outer_R));  // R*nz - R without cancellation
+  const float v0 = scene[0] - px, v1 = scene[1] - py, v2 = scene[2] - pz;
+  // direction towards the scene point in the tangent frame ex = (nz, 0, -nx)/|.|, ey = n x ex
+  const float f2 = nz * nz + nx * nx;
+  const float w = rsqrtf((v0 * v0 + v1 * v1 + v2 * v2) * f2);
+  const float ndx = (v0 * nz - v2 * nx) * w;
+  const float ndy = (f2 * v1 - ny * (nx * v0 + nz * v2)) * w;
+  const float do0 = ndx - s.out[2], do1 = ndy - s.out[3];
+  s.sqr_err = do0 * do0 + do1 * do1;
+  const float go = 0.72f * t_rcp(K[0] * K[3] - K[1] * K[2]);
+  const float b0 = do0 * go, b1 = do1 * go;
+  s.x = fmaf(-K[1], b1, fmaf(K[3], b0, s.x));
+  s.y = fmaf(K[0], b1, fmaf(-K[2], b0, s.y));
+  int error = s.error;
+  if (s.sqr_err > prev_sqr_err) error |= 1;
+  if (s.sqr_ap_err > prev_sqr_ap_err) error |= 2;
+  if (px != px) error |= 4;
+  if (r2 > cam.outer_pupil_r2) error |= 16;
+  if (s.k < 10) error = 0;  // "error reset (k<10)", tests/aperture_sampling_debug/writout.txt:40
+  s.error = error;
+  s.k += 1;
+}
 template <typename T, typename E, typename C>
 LB_DEV void lt_iterate(const E &ev, const C &cam, const T scene[3], T ax, T ay, T lambda, LtState<T> &s) {
   const T b[5] = {s.x, s.y, s.dx, s.dy, lambda};
   T ap[2], J[4], K[4];
   ev.lt_all(b, ap, J, s.out, K);
+#ifndef LB_GENERIC_LT_TAIL
+  if constexpr (sizeof(T) == 4) {
+    if (cam.outer_geom == 0) {
+      lt_iterate_tail_sphere(cam, scene, ax, ay, ap, J, K, s);
+      return;
+    }
+  }
+#endif
   lt_iterate_tail(cam, scene, ax, ay, ap, J, K, s);
 }
 // half of a packed pair (two-rays-per-thread forward kernel, camera_kernels.cuh)

@@ -215,6 +215,10 @@ void refresh_consts(lb_camera *c) {
     using T = decltype(k.lambda);
     k.sensor_half = T((double)p.sensor_width * 0.5);
     k.lambda = T(s.lambda);
+    k.lambda_exact = s.lambda;
+    k.inv_outer_R = T(1.0 / s.lens_outer_pupil_curvature_radius);
+    k.abs_inv_outer_R = T(1.0 / std::fabs(s.lens_outer_pupil_curvature_radius));
+    k.outer_R2 = T(s.lens_outer_pupil_curvature_radius * s.lens_outer_pupil_curvature_radius);
     k.aperture_radius = T(s.aperture_radius);
     k.sensor_shift = T(s.sensor_shift);
     k.outer_R = T(s.lens_outer_pupil_curvature_radius);
@@ -271,12 +275,45 @@ cudaError_t launch_rays(lb_camera *c, const RayIO &io, size_t n, uint64_t ray_id
   return launch_create_rays(c->lens_kernel, c->lens, c->camf, io, n, ray_id_base, stream);
 }
 
-// get_lentil_camera_params (lentil.h:1189-1243) + camera_model_specific_setup (lentil.h:1568-1670)
+template <typename T>
+struct DevBuf {  // device scratch freed on every exit path
+  T *p = nullptr;
+  ~DevBuf() { cudaFree(p); }
+  cudaError_t alloc(size_t n) { return cudaMalloc(&p, n * sizeof(T)); }
+};
+
+// get_lentil_camera_params (lentil.h:1189-1243) + camera_model_specific_setup (lentil.h:1568-1670).
+// Transactional: a failure (unknown lens, bad bokeh image, CUDA error) leaves the camera in its previous valid state.
+int camera_setup_impl(lb_camera *c, const lb_camera_params *p, const lb_bokeh_image *bokeh);
 int camera_setup(lb_camera *c, const lb_camera_params *p, const lb_bokeh_image *bokeh) {
+  struct Saved {
+    lb_camera_params params; lb_camera_state st; LensTable lens; int lens_kernel; CamConsts<float> camf; ThinConsts thin; CamConsts<double> camd;
+    float *cdf_row, *cdf_col; int32_t *row_idx, *col_idx; int bokeh_n;
+  };
+  Saved *old = new Saved{c->params, c->st, c->lens, c->lens_kernel, c->camf, c->thin, c->camd, c->d_cdf_row, c->d_cdf_col, c->d_row_idx, c->d_col_idx, c->bokeh_n};
+  // the new tables are built beside the old ones; whichever set loses is freed below
+  c->d_cdf_row = c->d_cdf_col = nullptr;
+  c->d_row_idx = c->d_col_idx = nullptr;
+  c->bokeh_n = 0;
+  const int rc = camera_setup_impl(c, p, bokeh);
+  if (rc != LB_OK) {
+    free_bokeh(c);
+    c->params = old->params; c->st = old->st; c->lens = old->lens; c->lens_kernel = old->lens_kernel; c->camf = old->camf; c->thin = old->thin; c->camd = old->camd;
+    c->d_cdf_row = old->cdf_row; c->d_cdf_col = old->cdf_col; c->d_row_idx = old->row_idx; c->d_col_idx = old->col_idx; c->bokeh_n = old->bokeh_n;
+  } else {
+    cudaDeviceSynchronize();  // launches that still read the previous tables
+    cudaFree(old->cdf_row); cudaFree(old->cdf_col); cudaFree(old->row_idx); cudaFree(old->col_idx);
+  }
+  delete old;
+  return rc;
+}
+int camera_setup_impl(lb_camera *c, const lb_camera_params *p, const lb_bokeh_image *bokeh) {
+  LensTable table;
+  if (!build_lens_table(p->lens_model, table)) return fail(LB_ERR_LENS, "unknown lens_model %d", p->lens_model);
+  c->lens = table;
   c->params = *p;
   lb_camera_state &s = c->st;
   memset(&s, 0, sizeof s);
-  if (!build_lens_table(p->lens_model, c->lens)) return fail(LB_ERR_LENS, "unknown lens_model %d", p->lens_model);
   const LpLens &L = LP_LENSES[p->lens_model];
   s.lens_outer_pupil_radius = L.c[C_OUTER_R];
   s.lens_inner_pupil_radius = L.c[C_INNER_R];
@@ -301,7 +338,6 @@ int camera_setup(lb_camera *c, const lb_camera_params *p, const lb_bokeh_image *
   c->lens_kernel = (has_unrolled_kernel(p->lens_model) && !(force_table && force_table[0] == '1')) ? p->lens_model : -1;
 
   // bokeh image -> CDF tables (lentil.h:222-228)
-  free_bokeh(c);
   if (p->bokeh_enable_image) {
     BokehTables bt;
     if (!bt.build(bokeh)) return fail(LB_ERR_IMAGE, "bokeh image missing, not square or < 3 channels");
@@ -323,12 +359,11 @@ int camera_setup(lb_camera *c, const lb_camera_params *p, const lb_bokeh_image *
       s.aperture_radius = s.lens_aperture_radius_at_fstop;
     } else {
       const int maxrays = 1000;
-      double4 *d_out = nullptr;
-      CU(cudaMalloc(&d_out, maxrays * sizeof(double4)));
-      CU(launch_fstop_rays(c->lens, c->camd, maxrays, s.lens_outer_pupil_radius, d_out, nullptr));
+      DevBuf<double4> out;
+      CU(out.alloc(maxrays));
+      CU(launch_fstop_rays(c->lens, c->camd, maxrays, s.lens_outer_pupil_radius, out.p, nullptr));
       std::vector<double4> h(maxrays);
-      CU(cudaMemcpy(h.data(), d_out, maxrays * sizeof(double4), cudaMemcpyDeviceToHost));
-      cudaFree(d_out);
+      CU(cudaMemcpy(h.data(), out.p, maxrays * sizeof(double4), cudaMemcpyDeviceToHost));
       // sequential selection of trace_backwards_for_fstop (lentil.h:1395-1440)
       double best_fstop = 0.0, best_radius = 0.0, calc_radius = 0.0;
       bool returned = false;
@@ -349,10 +384,12 @@ int camera_setup(lb_camera *c, const lb_camera_params *p, const lb_bokeh_image *
     {
       const std::vector<double> shifts = logarithmic_values();
       const int n = (int)shifts.size();
-      double *d_shifts = nullptr;
-      double4 *d_out = nullptr;
-      CU(cudaMalloc(&d_shifts, (n + 1) * sizeof(double)));
-      CU(cudaMalloc(&d_out, (n + 1) * sizeof(double4)));
+      DevBuf<double> shifts_buf;
+      DevBuf<double4> out_buf;
+      CU(shifts_buf.alloc(n + 1));
+      CU(out_buf.alloc(n + 1));
+      double *d_shifts = shifts_buf.p;
+      double4 *d_out = out_buf.p;
       CU(cudaMemcpy(d_shifts, shifts.data(), n * sizeof(double), cudaMemcpyHostToDevice));
       const double ap_y = s.lens_aperture_housing_radius * 0.25;
       CU(launch_focus_distances(c->lens, c->camd, ap_y, d_shifts, n, d_out, nullptr));
@@ -372,8 +409,6 @@ int camera_setup(lb_camera *c, const lb_camera_params *p, const lb_bokeh_image *
       s.focus_check_ok = chk.y > 0.0 && !(chk.z > s.lens_outer_pupil_radius * s.lens_outer_pupil_radius) &&
                          !(chk.w > s.lens_inner_pupil_radius * s.lens_inner_pupil_radius);
       s.focus_check_distance = s.focus_check_ok ? chk.x : 0.0;
-      cudaFree(d_shifts);
-      cudaFree(d_out);
     }
     s.tan_fov = std::tan(s.lens_field_of_view / 2.0);
   } else {  // ThinLens (lentil.h:1663-1668)
@@ -383,12 +418,6 @@ int camera_setup(lb_camera *c, const lb_camera_params *p, const lb_bokeh_image *
   }
   refresh_consts(c);
   return LB_OK;
-}
-
-bool is_device_ptr(const void *p) {
-  cudaPointerAttributes a;
-  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
-  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
 }  // namespace
@@ -418,7 +447,7 @@ void lb_camera_params_default(lb_camera_params *p) {  // lentil_camera.cpp:19-52
 int lb_lens_count(void) { return LP_LENS_COUNT; }
 const char *lb_lens_name(int m) { return (m >= 0 && m < LP_LENS_COUNT) ? LP_LENSES[m].name : nullptr; }
 const char *lb_last_error(void) { return g_last_error.c_str(); }
-const char *lb_version(void) { return "lentil_b200 0.2.0 (sm_100a)"; }
+const char *lb_version(void) { return "lentil_b200 0.3.0 (sm_100a)"; }
 
 int lb_camera_create(const lb_camera_params *params, const lb_bokeh_image *bokeh, int device, lb_camera **out) {
   if (!params || !out) return fail(LB_ERR_INVALID, "null argument");
@@ -461,11 +490,13 @@ void lb_camera_destroy(lb_camera *c) {
 
 int lb_camera_get_state(const lb_camera *c, lb_camera_state *out) {
   if (!c || !out) return fail(LB_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lk(const_cast<lb_camera *>(c)->mu);
   *out = c->st;
   return LB_OK;
 }
 int lb_camera_set_state(lb_camera *c, double aperture_radius, double sensor_shift) {
   if (!c) return fail(LB_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lk(c->mu);
   c->st.aperture_radius = aperture_radius;
   c->st.sensor_shift = sensor_shift;
   refresh_consts(c);
@@ -474,6 +505,7 @@ int lb_camera_set_state(lb_camera *c, double aperture_radius, double sensor_shif
 
 int lb_camera_set_pupil_geometry(lb_camera *c, int outer_geometry, int inner_geometry) {
   if (!c || outer_geometry < 0 || outer_geometry > 2 || inner_geometry < 0 || inner_geometry > 2) return fail(LB_ERR_INVALID, "geometry must be 0, 1 or 2");
+  std::lock_guard<std::mutex> lk(c->mu);
   c->st.outer_pupil_geometry = outer_geometry;
   c->st.inner_pupil_geometry = inner_geometry;
   refresh_consts(c);
@@ -505,6 +537,7 @@ int lb_camera_create_rays(lb_camera *c, size_t n, uint64_t ray_id_base, const lb
   if (!c || !in || !out) return fail(LB_ERR_INVALID, "null argument");
   if (n == 0) return LB_OK;
   if (!in->sx || !in->sy || !in->dsx || !in->dsy || !in->lensx || !in->lensy) return fail(LB_ERR_INVALID, "null input array");
+  std::lock_guard<std::mutex> lk(c->mu);  // the launch reads camf / the lens table / the bokeh pointers: not under a concurrent lb_camera_update
   DeviceGuard g(c->device);
   RayIO io{in->sx, in->sy, in->dsx, in->dsy, in->lensx, in->lensy, out->origin, out->dir, out->dOdx, out->dOdy,
            out->dDdx, out->dDdy, out->weight, out->tries, n};

@@ -102,6 +102,7 @@ struct SampleIO {
   float inv_density;
   const uint8_t *crypto_count;   // [n] or NULL
   const float *crypto_opacity;   // [n][crypto_depth] or NULL
+  float w2c[4][3];               // world_to_camera_matrix of the batch (columns 0..2 of the AtMatrix; identity by default)
 };
 
 struct WorkItem {  // one redistributed source sample
@@ -126,12 +127,17 @@ cudaError_t launch_filter_splat(int lens_kernel, const LensTable &lens, const Ca
 cudaError_t launch_closest_gather(const FilterConsts &fc, const AovSet &aovs, const SampleIO &s, uint64_t sample_base,
                                   cudaStream_t stream);
 // ranked cryptomatte resolve of one bucket (lentil_imager.cpp:122-161); out is read-modify-write
+// brk != NULL: no row ends early; instead brk[pixel] = 1 marks the pixels that hold <= rank ids (they are not written), so the
+// caller can end bucket rows itself (out and brk are then indexed like the frame: w == xres, x0 == y0 == 0)
 cudaError_t launch_resolve_crypto(const uint32_t *key, const float *wgt, const float4 *total, int slots, int rank, int xres, int x0, int y0,
-                                  int w, int h, float4 *out, cudaStream_t stream);
+                                  int w, int h, float4 *out, uint8_t *brk, cudaStream_t stream);
 // multi-GPU: fold another rank's tables into this rank's
 cudaError_t launch_crypto_merge(uint32_t *key, float *wgt, const uint32_t *other_key, const float *other_wgt, size_t npx, int slots,
                                 FilterCounters *counters, cudaStream_t stream);
 cudaError_t launch_resolve(const float4 *buffer, const float *weight, int filter, int role, int xres, int x0, int y0, int w, int h,
                            float4 *out, cudaStream_t stream);
+// same for the pixel range [first, first + count) of the frame, out[0] = pixel `first`
+cudaError_t launch_resolve_linear(const float4 *buffer, const float *weight, int filter, int role, size_t first, size_t count, float4 *out,
+                                  cudaStream_t stream);
 
 }  // namespace lb

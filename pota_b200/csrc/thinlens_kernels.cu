@@ -162,7 +162,7 @@ k_create_rays_thinlens(const __grid_constant__ CamConsts<float> cam, const __gri
   const float sx = __ldg(io.sx + i), sy = __ldg(io.sy + i);
   const float dsx = __ldg(io.dsx + i), dsy = __ldg(io.dsy + i);
   float r1 = __ldg(io.lensx + i), r2 = __ldg(io.lensy + i);
-  const uint32_t ray_id = (uint32_t)(ray_id_base + i);
+  const uint32_t ray_id = ray_seed_word(ray_id_base + i);
   // the thin-lens trace is exact float arithmetic on both sides: the reference's own step is kept (no baseline stretch)
   const float step = 0.001f;
   int tries, td;

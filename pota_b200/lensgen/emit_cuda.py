@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import os
 
+from . import emit_folded
 from .emit import derivative
 from .pack import load_pack
 
@@ -210,6 +211,14 @@ def emit_group(name, signature, polys, outputs, packed=False, acc=2):
 
 
 def lens_unit(lens) -> tuple[str, dict]:
+    """One translation unit per lens.  Kernels:
+      k_create_rays_<k>          K1, wavelength-folded two-ray packed bodies, coefficients from a __grid_constant__ table
+      k_create_rays_w550_<k>     K1, the same bodies folded at the default wavelength (550 nm) into immediates
+      k_filter_splat_<k>         K2, wavelength-folded mirror-packed body, coefficient table
+      k_filter_splat_w550_<k>    K2, folded at 550 nm into immediates
+      k_filter_splat_chroma_<k>  K2, first-generation 5-variate scalar body: chromatic aberration gives every lane its own
+                                 wavelength (lentil_filter.cpp:254-267)
+    """
     k = lens["index"]
     P = {n: [(float(c), list(e)) for c, e in terms] for n, terms in lens["polys"].items()}
 
@@ -220,22 +229,13 @@ def lens_unit(lens) -> tuple[str, dict]:
     dout = [d("out_dx", 0), d("out_dx", 1), d("out_dy", 0), d("out_dy", 1)]
     src = ["// generated by pota_b200.lensgen.emit_cuda from pota_b200/lenses/%s.json -- do not edit" % lens["lens_id"],
            '#include "../camera_kernels.cuh"', '#include "../filter_kernels%s.cuh"' % ("_packed" if K2_PACKED else ""), '#include "../unrolled_dispatch.h"', "",
-           "namespace lb {", "namespace {", "", "struct Eval%d {" % k]
+           "namespace lb {", "namespace {", "", "struct Eval%d {  // 5-variate bodies (wavelength as a variable)" % k]
     stats = {}
-    body, mul, ffma = emit_group("ap_jac", "const float b[5], float ap[2], float J[4]", [P["ap_x"], P["ap_y"]] + dap,
-                                 ["ap[0]", "ap[1]", "J[0]", "J[1]", "J[2]", "J[3]"])
-    src += body
-    stats["ap_jac"] = (mul, ffma)
-    body, mul, ffma = emit_group("out5", "const float b[5], float out[4], float &T", [P["out_x"], P["out_y"], P["out_dx"], P["out_dy"], P["out_t"]],
-                                 ["out[0]", "out[1]", "out[2]", "out[3]", "T"])
-    src += body
-    stats["out5"] = (mul, ffma)
-    body, _, _ = emit_group("ap_jac2", "const float2 b[5], float2 ap[2], float2 J[4]", [P["ap_x"], P["ap_y"]] + dap,
-                            ["ap[0]", "ap[1]", "J[0]", "J[1]", "J[2]", "J[3]"], packed=True)
-    src += body
-    body, _, _ = emit_group("out5_2", "const float2 b[5], float2 out[4], float2 &T", [P["out_x"], P["out_y"], P["out_dx"], P["out_dy"], P["out_t"]],
-                            ["out[0]", "out[1]", "out[2]", "out[3]", "T"], packed=True)
-    src += body
+    # op statistics of the first-generation K1 bodies (kept for the comparison in tests / DESIGN; not emitted any more)
+    for name, polys, outs in (("ap_jac", [P["ap_x"], P["ap_y"]] + dap, ["ap[0]", "ap[1]", "J[0]", "J[1]", "J[2]", "J[3]"]),
+                              ("out5", [P["out_x"], P["out_y"], P["out_dx"], P["out_dy"], P["out_t"]], ["out[0]", "out[1]", "out[2]", "out[3]", "T"])):
+        _, mul, ffma = emit_group(name, "", polys, outs)
+        stats[name] = (mul, ffma)
     body, mul, ffma = emit_group("transmittance_", "const float b[5], float &T", [P["out_t"]], ["T"])
     src += body
     src += ["  LB_DEV float transmittance(const float b[5]) const { float T; transmittance_(b, T); return T; }"]
@@ -251,24 +251,55 @@ def lens_unit(lens) -> tuple[str, dict]:
                                 ["ap[0]", "ap[1]", "J[0]", "J[1]", "J[2]", "J[3]", "out[0]", "out[1]", "out[2]", "out[3]", "K[0]", "K[1]", "K[2]", "K[3]"],
                                 packed=True, acc=PACKED_ACC)
         src += body
-    src += ["};", "",
+    src += ["};", ""]
+    # second generation: wavelength folded into the coefficients (emit_folded.py); K1 two-ray packed, K2 mirror packed
+    for imm in (None, emit_folded.LAMBDA_550):
+        fsrc, fstats, _, _ = emit_folded.folded_evaluators(lens, imm_lambda=imm)
+        src += fsrc
+        stats.update({g: (v if isinstance(v, tuple) else (v["fmul"] + v["fmul2"], v["ffma"] + v["ffma2"])) for g, v in fstats.items()})
+    splat = "splat_persistent%s" % ("2" if K2_PACKED else "")
+    k1_sig = "(const __grid_constant__ CamConsts<float> cam, const __grid_constant__ RayIO io, size_t n, uint64_t ray_id_base"
+    k2_sig = ("(const __grid_constant__ CamConsts<float> cam, const __grid_constant__ FilterConsts fc, const __grid_constant__ AovSet aovs,\n"
+              "    const __grid_constant__ SampleIO s, const WorkItem *__restrict__ work, FilterCounters *__restrict__ counters, uint64_t sample_base")
+    k1_body = ["  const size_t j = (size_t)blockIdx.x * 128 + threadIdx.x;  // rays j and j + ceil(n/2)", "  if (j >= (n + 1) / 2) return;"]
+    src += ["__global__ void __launch_bounds__(128%s)" % K1F_MIN_BLOCKS,
+            "k_create_rays_%d%s, const __grid_constant__ FoldA%d C) {" % (k, k1_sig, k)] + k1_body + [
+            "  camera_create_ray_pair(EvalFA%d{C}, cam, io, j, n, ray_id_base);" % k, "}", "",
             "__global__ void __launch_bounds__(128%s)" % K1_MIN_BLOCKS,
-            "k_create_rays_%d(const __grid_constant__ CamConsts<float> cam, const __grid_constant__ RayIO io, size_t n, uint64_t ray_id_base) {" % k,
-            "  const size_t j = (size_t)blockIdx.x * 128 + threadIdx.x;  // rays j and j + ceil(n/2)",
-            "  if (j >= (n + 1) / 2) return;",
-            "  camera_create_ray_pair(Eval%d{}, cam, io, j, n, ray_id_base);" % k,
-            "}", "",
+            "k_create_rays_w550_%d%s) {" % (k, k1_sig)] + k1_body + [
+            "  camera_create_ray_pair(EvalIA%d{}, cam, io, j, n, ray_id_base);" % k, "}", "",
+            "__global__ void __launch_bounds__(128%s)" % K2F_MIN_BLOCKS,
+            "k_filter_splat_%d%s, const __grid_constant__ FoldB%d C) {" % (k, k2_sig, k),
+            "  splat_persistent(EvalFB%d{C}, cam, fc, aovs, s, work, counters, sample_base);" % k, "}", "",
+            "__global__ void __launch_bounds__(128%s)" % K2F_MIN_BLOCKS,
+            "k_filter_splat_w550_%d%s) {" % (k, k2_sig),
+            "  splat_persistent(EvalIB%d{}, cam, fc, aovs, s, work, counters, sample_base);" % k, "}", "",
             "__global__ void __launch_bounds__(128%s)" % K2_MIN_BLOCKS,
-            "k_filter_splat_%d(const __grid_constant__ CamConsts<float> cam, const __grid_constant__ FilterConsts fc, const __grid_constant__ AovSet aovs," % k,
-            "                  const __grid_constant__ SampleIO s, const WorkItem *__restrict__ work, FilterCounters *__restrict__ counters, uint64_t sample_base) {",
-            "  splat_persistent%s(Eval%d{}, cam, fc, aovs, s, work, counters, sample_base);" % ("2" if K2_PACKED else "", k),
-            "}", "", "}  // namespace", "",
+            "k_filter_splat_chroma_%d%s) {" % (k, k2_sig),
+            "  %s(Eval%d{}, cam, fc, aovs, s, work, counters, sample_base);" % (splat, k), "}", "",
+            "constexpr double kLambda550 = 550.0 * 0.001;  // `wavelength * 0.001` of the default parameter (lentil.h:1213)",
+            "}  // namespace", "",
             "cudaError_t launch_fw_lens_%d(const CamConsts<float> &cam, const RayIO &io, size_t n, uint64_t ray_id_base, cudaStream_t stream) {" % k,
-            "  k_create_rays_%d<<<(unsigned)(((n + 1) / 2 + 127) / 128), 128, 0, stream>>>(cam, io, n, ray_id_base);" % k,
+            "  const unsigned grid = (unsigned)(((n + 1) / 2 + 127) / 128);",
+            "  if (cam.lambda_exact == kLambda550 && kernel_generation() == 2) {",
+            "    k_create_rays_w550_%d<<<grid, 128, 0, stream>>>(cam, io, n, ray_id_base);" % k,
+            "  } else {  // wavelength folded into the coefficients on the host, once per launch",
+            "    FoldA%d C;" % k,
+            "    fold_a%d(cam.lambda_exact, C);" % k,
+            "    k_create_rays_%d<<<grid, 128, 0, stream>>>(cam, io, n, ray_id_base, C);" % k,
+            "  }",
             "  return cudaGetLastError();", "}",
             "cudaError_t launch_bw_lens_%d(const CamConsts<float> &cam, const FilterConsts &fc, const AovSet &aovs, const SampleIO &s, const WorkItem *work," % k,
             "                             FilterCounters *counters, uint64_t sample_base, int grid, cudaStream_t stream) {",
-            "  k_filter_splat_%d<<<grid, 128, 0, stream>>>(cam, fc, aovs, s, work, counters, sample_base);" % k,
+            "  if (fc.abb_chromatic > 0.0f || kernel_generation() == 0) {",
+            "    k_filter_splat_chroma_%d<<<grid, 128, 0, stream>>>(cam, fc, aovs, s, work, counters, sample_base);" % k,
+            "  } else if (cam.lambda_exact == kLambda550 && kernel_generation() == 2) {",
+            "    k_filter_splat_w550_%d<<<grid, 128, 0, stream>>>(cam, fc, aovs, s, work, counters, sample_base);" % k,
+            "  } else {",
+            "    FoldB%d C;" % k,
+            "    fold_b%d(cam.lambda_exact, C);" % k,
+            "    k_filter_splat_%d<<<grid, 128, 0, stream>>>(cam, fc, aovs, s, work, counters, sample_base, C);" % k,
+            "  }",
             "  return cudaGetLastError();", "}", "", "}  // namespace lb", ""]
     return "\n".join(src), stats
 
@@ -280,6 +311,8 @@ def lens_unit(lens) -> tuple[str, dict]:
 # the lexicographic bodies 7.01e8 at 4, 7.43e8 at 5 (96 registers, no spill), 7.44e8 at 6 (80, spills).
 K1_MIN_BLOCKS = ", " + os.environ.get("LB_K1_MINBLOCKS", "4")
 K2_MIN_BLOCKS = ", " + os.environ.get("LB_K2_MINBLOCKS", "5")
+K1F_MIN_BLOCKS = ", " + os.environ.get("LB_K1F_MINBLOCKS", "4")
+K2F_MIN_BLOCKS = ", " + os.environ.get("LB_K2F_MINBLOCKS", "5")
 K2_PACKED = os.environ.get("LB_K2_PACKED", "0") == "1"  # experimental, see csrc/filter_kernels_packed.cuh
 PACKED_ACC = int(os.environ.get("LB_PACKED_ACC", "2"))  # accumulators per long polynomial of lt_all2 (register pressure knob)
 

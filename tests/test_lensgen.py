@@ -90,3 +90,96 @@ def test_upstream_headers_are_emitted_for_every_lens(tmp_path):
         for f in ("pt_evaluate.h", "pt_sample_aperture.h", "lt_sample_aperture.h", "lens_constants.h"):
             p = tmp_path / "polynomial-optics" / "database" / "lenses" / d / "code" / f
             assert p.exists() and p.read_text().startswith("case ")
+
+
+# ---- second-generation bodies (wavelength folded, K1 two-ray packed / K2 mirror packed) ------------------------
+@pytest.fixture(scope="module")
+def folded_host_lib(tmp_path_factory):
+    """The generated EvalFA / EvalFB source lines compiled by g++ against a float2 stand-in (no GPU needed)."""
+    import ctypes
+    import subprocess
+
+    from pota_b200.lensgen import emit_folded
+
+    d = tmp_path_factory.mktemp("folded")
+    libs = {}
+    for name, imm in (("table", None), ("imm550", emit_folded.LAMBDA_550)):  # coefficient-table bodies / 550 nm immediates
+        src = d / f"folded_{name}.cpp"
+        src.write_text(emit_folded.host_test_source(FOLDED_TEST_LENSES, imm_lambda=imm))
+        so = d / f"libfolded_{name}.so"
+        subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", "-o", str(so), str(src)], check=True)
+        libs[name] = ctypes.CDLL(str(so))
+    return libs
+
+
+FOLDED_TEST_LENSES = [5, 12, 28, 43]
+
+
+@pytest.mark.parametrize("lens_index", FOLDED_TEST_LENSES)
+@pytest.mark.parametrize("lam,kind", [(0.55, "table"), (0.42, "table"), (0.7, "table"), (550.0 * 0.001, "imm550")])
+def test_folded_bodies_match_direct_evaluation(folded_host_lib, lens_index, lam, kind):
+    """Every output of the mirror-packed lt_all and of the two-ray packed ap_jac2 / out5_2, against the pack's polynomials
+    evaluated term by term in double at the same wavelength."""
+    import ctypes
+
+    L = folded_host_lib[kind]
+    lens = pack.load_pack()[lens_index]
+    P = {n: [(c, tuple(e)) for c, e in t] for n, t in lens["polys"].items()}
+    d = lambda n, v: [(c, tuple(e)) for c, e in emit.derivative(P[n], v)]  # noqa: E731
+    lt = [P["ap_x"], P["ap_y"], d("ap_x", 2), d("ap_x", 3), d("ap_y", 2), d("ap_y", 3), P["out_x"], P["out_y"], P["out_dx"], P["out_dy"],
+          d("out_dx", 0), d("out_dx", 1), d("out_dy", 0), d("out_dy", 1)]
+    rs = np.random.default_rng(100 + lens_index)
+    n = 48
+    X = np.stack([rs.uniform(-10, 10, n), rs.uniform(-8, 8, n), rs.uniform(-0.25, 0.25, n), rs.uniform(-0.25, 0.25, n), np.full(n, lam)])
+    X[:, 0] = [3.0, -2.0, 0.0, 0.1, lam]  # an axis-aligned point: mirror halves differ strongly
+    X32 = X.astype(np.float32).astype(np.float64)
+    X32[4] = lam
+
+    def scale(terms):  # sum of |term|: what float32 rounding is relative to
+        s = np.zeros(n)
+        for c, e in terms:
+            s += np.abs(c * np.prod([X32[k] ** e[k] for k in range(5)], axis=0))
+        return s + 1e-30
+
+    fp = ctypes.POINTER(ctypes.c_float)
+    for i in range(n):
+        b = np.array(list(X32[:4, i]) + [lam], np.float32)
+        out = np.zeros(14, np.float32)
+        assert L.ft_lt_all(lens_index, ctypes.c_double(lam), b.ctypes.data_as(fp), out.ctypes.data_as(fp)) == 0
+        for j, terms in enumerate(lt):
+            want = poly_eval(terms, X32[:, i:i + 1])[0]
+            assert abs(out[j] - want) <= 4e-6 * scale(terms)[i], (lens_index, j, i, out[j], want)
+        t = np.zeros(1, np.float32)
+        assert L.ft_transmittance(lens_index, ctypes.c_double(lam), b.ctypes.data_as(fp), t.ctypes.data_as(fp)) == 0
+        assert abs(t[0] - poly_eval(P["out_t"], X32[:, i:i + 1])[0]) <= 4e-6 * scale(P["out_t"])[i]
+    # two-ray packed bodies: points i and i+1 in the two halves
+    for i in range(0, n, 2):
+        b2 = np.zeros((5, 2), np.float32)
+        b2[:4] = X32[:4, i:i + 2]
+        b2[4] = lam
+        aj = np.zeros((6, 2), np.float32)
+        assert L.ft_ap_jac2(lens_index, ctypes.c_double(lam), b2.ctypes.data_as(fp), aj.ctypes.data_as(fp)) == 0
+        o5 = np.zeros((5, 2), np.float32)
+        assert L.ft_out5_2(lens_index, ctypes.c_double(lam), b2.ctypes.data_as(fp), o5.ctypes.data_as(fp)) == 0
+        for h in range(2):
+            for j, terms in enumerate(lt[:6]):
+                want = poly_eval(terms, X32[:, i + h:i + h + 1])[0]
+                assert abs(aj[j, h] - want) <= 4e-6 * scale(terms)[i + h], (lens_index, j, i, h)
+            for j, terms in enumerate([P["out_x"], P["out_y"], P["out_dx"], P["out_dy"], P["out_t"]]):
+                want = poly_eval(terms, X32[:, i + h:i + h + 1])[0]
+                assert abs(o5[j, h] - want) <= 4e-6 * scale(terms)[i + h], (lens_index, j, i, h)
+
+
+def test_folded_bodies_issue_fewer_operations():
+    """What the second generation is for: the mirror-packed lt_all issues about half the instructions of the 5-variate
+    scalar body, and the folded K1 bodies fewer FMA-pipe operations than the 5-variate packed ones."""
+    from pota_b200.lensgen import emit_folded
+
+    for k in (5, 43):
+        _, st = emit_cuda.lens_unit(pack.load_pack()[k])
+        assert sum(st["lt_all_mirror"]) < 0.6 * sum(st["lt_all"])
+        assert sum(st["ap_jac2_folded"]) < 0.92 * sum(st["ap_jac"]) and sum(st["out5_2_folded"]) < 0.92 * sum(st["out5"])
+        _, fst, _, cb = emit_folded.folded_evaluators(pack.load_pack()[k])
+        m = fst["lt_all_mirror"]
+        # FMA-pipe lane operations (packed instructions count two) stay at or below the scalar body's
+        assert 2 * (m["fmul2"] + m["ffma2"]) + m["fmul"] + m["ffma"] <= sum(st["lt_all"])
