@@ -182,6 +182,13 @@ LB_API int lb_bench_fp32_peak(int device, double *tflops_out);
  * plane, in GB/s: roofline denominator of the splat accumulate. */
 LB_API int lb_bench_red_peak(int device, int megabytes, double *gbytes_per_s_out);
 
+/* Known-answer hook for the device-side integer / float primitives (global.h:32-57 tea<8> and rng, lens.h:17-37
+ * fast_sin / fast_cos): for n seed pairs (v0, v1) computes on the device t = tea<8>(v0, v1), four rng() draws seeded
+ * with t (state after each draw and the float), and fast_sin / fast_cos of (first draw - 0.5) * 20.  HOST arrays:
+ * tea_out [n], lcg_state_out / lcg_float_out [n][4], trig_out [n][2]. */
+LB_API int lb_debug_primitives(int device, size_t n, const uint32_t *v0, const uint32_t *v1, uint32_t *tea_out,
+                               uint32_t *lcg_state_out, float *lcg_float_out, float *trig_out);
+
 /* ---- filter / imager ---------------------------------------------------------------------- */
 
 /* AOVData::original_filter (lentil.h:827,832); LB_FILTER_CRYPTO marks an AOVData with is_crypto set

@@ -244,6 +244,10 @@ int ref_filter_accumulate(ref_camera *r, const lb_samples *S, int nthreads) {
   it.aovs["P"] = {P.data(), 3};
   it.aovs["Z"] = {Z.data(), 1};
   it.aovs["volume"] = {vol.data(), 3};
+  // The filter REQUIRES "FLOAT lentil_bidir_ignore" (lentil_filter.cpp:24) but READS atstring_lentil_ignore =
+  // "lentil_ignore" (lentil.h:184, lentil_filter.cpp:162).  LB_SAMPLE_IGNORE stands for the value read at :162, so the
+  // harness serves it under the name that line asks for (and under the required name, which nothing reads).
+  it.aovs["lentil_ignore"] = {ign.data(), 1};
   it.aovs["lentil_bidir_ignore"] = {ign.data(), 1};
   it.aovs["lentil_time"] = {zero.data(), 1};
   it.aovs["lentil_raydir"] = {S->raydir ? S->raydir : zero.data(), 3};

@@ -30,7 +30,7 @@ EXPORTS = [
     "lb_filter_begin", "lb_filter_accumulate", "lb_filter_accumulate_host", "lb_filter_get_stats",
     "lb_filter_newton_iterations", "lb_imager_resolve", "lb_imager_resolve_host", "lb_filter_buffers", "lb_filter_buffers_host", "lb_filter_crypto_host",
     "lb_bench_fp32_peak", "lb_bench_red_peak", "lb_camera_set_pupil_geometry", "lb_camera_kernel_kind", "lb_comm_unique_id", "lb_comm_init", "lb_filter_set_sample_base", "lb_filter_reduce", "lb_comm_destroy",
-    "lb_filter_reduce_scatter", "lb_filter_slab", "lb_imager_resolve_gather",
+    "lb_filter_reduce_scatter", "lb_filter_slab", "lb_imager_resolve_gather", "lb_debug_primitives",
 ]  # fmt: skip
 
 
@@ -83,6 +83,7 @@ def lib():
         L.lb_filter_reduce_scatter.argtypes = [vp, vp]
         L.lb_filter_slab.argtypes = [vp, C.POINTER(sz), C.POINTER(sz)]
         L.lb_imager_resolve_gather.argtypes = [vp, i, vp, i, vp]
+        L.lb_debug_primitives.argtypes = [i, sz, vp, vp, vp, vp, vp, vp]
         _lib = L
     return _lib
 

@@ -107,3 +107,53 @@ extern "C" int lb_bench_red_peak(int device, int megabytes, double *gbytes_per_s
   *gbytes_per_s_out = best;
   return cudaGetLastError() == cudaSuccess ? LB_OK : LB_ERR_CUDA;
 }
+
+// ---- known-answer hooks for the device primitives (tests only; the splat images pin them implicitly) --------------
+#include "lens_device.cuh"
+namespace {
+__global__ void k_debug_primitives(size_t n, const uint32_t *__restrict__ v0, const uint32_t *__restrict__ v1, uint32_t *__restrict__ tea_out,
+                                   uint32_t *__restrict__ lcg_state_out, float *__restrict__ lcg_float_out, float *__restrict__ trig_out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t t = lb::tea8(v0[i], v1[i]);
+  tea_out[i] = t;
+  uint32_t s = t;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    lcg_float_out[4 * i + k] = lb::lcg_rng(s);
+    lcg_state_out[4 * i + k] = s;
+  }
+  const float x = (lcg_float_out[4 * i] - 0.5f) * 20.0f;  // fast_sin / fast_cos argument in [-10, 10)
+  trig_out[2 * i] = lb::fast_sin(x);
+  trig_out[2 * i + 1] = lb::fast_cos(x);
+}
+}  // namespace
+
+// tea<8>(v0, v1), four LCG draws seeded with it (state + float), fast_sin / fast_cos of a value derived from the first
+// draw -- computed on the device.  All pointers are HOST arrays: v0, v1 [n]; tea_out [n]; lcg_state_out, lcg_float_out
+// [n][4]; trig_out [n][2].  (global.h:32-57, lens.h:17-37)
+extern "C" int lb_debug_primitives(int device, size_t n, const uint32_t *v0, const uint32_t *v1, uint32_t *tea_out, uint32_t *lcg_state_out,
+                                   float *lcg_float_out, float *trig_out) {
+  if (!v0 || !v1 || !tea_out || !lcg_state_out || !lcg_float_out || !trig_out) return LB_ERR_INVALID;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device >= ndev) return LB_ERR_NO_DEVICE;
+  if (n == 0) return LB_OK;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  cudaSetDevice(device);
+  uint32_t *d = nullptr;
+  const size_t words = n * (2 + 1 + 4 + 4 + 2);
+  if (cudaMalloc(&d, words * 4) != cudaSuccess) { cudaSetDevice(prev); return LB_ERR_CUDA; }
+  uint32_t *dv0 = d, *dv1 = d + n, *dt = d + 2 * n, *ds = d + 3 * n;
+  float *df = (float *)(d + 7 * n), *dg = (float *)(d + 11 * n);
+  cudaMemcpy(dv0, v0, n * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(dv1, v1, n * 4, cudaMemcpyHostToDevice);
+  k_debug_primitives<<<(unsigned)((n + 255) / 256), 256>>>(n, dv0, dv1, dt, ds, df, dg);
+  cudaMemcpy(tea_out, dt, n * 4, cudaMemcpyDeviceToHost);
+  cudaMemcpy(lcg_state_out, ds, n * 16, cudaMemcpyDeviceToHost);
+  cudaMemcpy(lcg_float_out, df, n * 16, cudaMemcpyDeviceToHost);
+  cudaMemcpy(trig_out, dg, n * 8, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  cudaSetDevice(prev);
+  return cudaGetLastError() == cudaSuccess ? LB_OK : LB_ERR_CUDA;
+}

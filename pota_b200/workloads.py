@@ -55,18 +55,40 @@ def camera_samples(width: int, height: int, spp: int, device="cpu", first: int =
     return dict(sx=sx.contiguous(), sy=sy.contiguous(), dsx=d, dsy=d.clone(), lensx=lensx.contiguous(), lensy=lensy.contiguous())
 
 
+def tile_partition(width: int, height: int, spp: int, rank: int, world: int, tile: int = 64, device="cpu") -> torch.Tensor:
+    """Sample indices (int64, k = (py*width + px)*spp + s) of the frame's samples that `rank` of `world` accumulates:
+    tile x tile pixel tiles dealt round-robin along both axes ("image tiles x sample ranges, round-robin
+    to GPUs"), so every rank gets its share of any bright region instead of a contiguous band of rows.  Ordered tile
+    by tile, row-major inside a tile, the spp samples of a pixel adjacent (the classify kernel merges runs of equal
+    pixels).  The union over ranks is every sample exactly once."""
+    py, px = torch.meshgrid(torch.arange(height, dtype=torch.int64, device=device), torch.arange(width, dtype=torch.int64, device=device), indexing="ij")
+    tx, ty = px // tile, py // tile
+    mine = ((tx + ty) % world) == rank
+    px, py, tx, ty = px[mine], py[mine], tx[mine], ty[mine]
+    tiles_x = -(-width // tile)
+    key = ((ty * tiles_x + tx) * tile + (py % tile)) * tile + (px % tile)
+    order = torch.argsort(key)
+    pix = (py * width + px)[order]
+    return (pix[:, None] * spp + torch.arange(spp, dtype=torch.int64, device=device)[None, :]).reshape(-1)
+
+
 def highlight_frame(width: int, height: int, spp: int, tan_fov: float, device="cpu", first: int = 0, count: int | None = None,
                     z_plane: float = 75.0, pitch: float = 5.4, radius: float = 0.133, grid=(16, 12), radiance: float = 84.1589,
-                    n_extra_aov: int = 0):
+                    n_extra_aov: int = 0, samples: torch.Tensor | None = None):
     """Synthetic HDR frame of config C3, modelled on /root/reference/tests/cuda/lightgrid.ass: a black
     background at Z = inf plus a grid of emissive discs on the plane z_cs = -z_plane.  One sample per
     (pixel, s); the sample position comes from a pinhole ray through the jittered pixel position.
 
+    `samples`: explicit sample indices (e.g. tile_partition) instead of the range [first, first + count).
     Returns dict(px, py int32 [n]; rgba, pos_cs float32 [n,4]; aov_values list of [n,4]).
     """
     total = width * height * spp
-    count = total - first if count is None else count
-    k = torch.arange(first, first + count, dtype=torch.int64, device=device)
+    if samples is not None:
+        k = samples.to(device=device, dtype=torch.int64)
+        count = int(k.numel())
+    else:
+        count = total - first if count is None else count
+        k = torch.arange(first, first + count, dtype=torch.int64, device=device)
     pix = k // spp
     s = k % spp
     px = pix % width

@@ -1,5 +1,15 @@
-"""Print the roofline-relevant counters of an .ncu-rep (first profiled launch)."""
+"""Print the roofline-relevant counters of an .ncu-rep (first profiled launch).
+
+    python scripts/ncusum.py REPORT.ncu-rep
+    python scripts/ncusum.py REPORT.ncu-rep --traffic k_create_rays --units 33177600 [--out profiles/kernel_traffic.json]
+
+--traffic records dram__bytes_read.sum + dram__bytes_write.sum of the captured launch per unit (ray / splat) together with
+the hash of the kernel's sources (bench.kernel_source_hash) in a JSON file that bench.py reads for `roofline.traffic`;
+a capture taken on older sources is detected there as stale.
+"""
 import csv
+import json
+import os
 import subprocess
 import sys
 
@@ -21,3 +31,31 @@ for i, h in enumerate(hdr):
     if h in want or (h.startswith("smsp__average_warps_issue_stalled") and h.endswith("_per_issue_active.ratio")) or \
             (h.startswith("smsp__average_warp_latency_issue_stalled") and h.endswith(".ratio")):
         print(f"{h} = {vals[i]} {units[i]}")
+
+
+def _num(name):
+    i = hdr.index(name)
+    v = float(vals[i].replace(",", ""))
+    u = units[i].lower()
+    return v * {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9, "tbyte": 1e12}.get(u, 1.0)
+
+
+if "--traffic" in sys.argv:
+    key = sys.argv[sys.argv.index("--traffic") + 1]
+    n_units = float(sys.argv[sys.argv.index("--units") + 1])
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = sys.argv[sys.argv.index("--out") + 1] if "--out" in sys.argv else os.path.join(root, "profiles", "kernel_traffic.json")
+    sys.path.insert(0, root)
+    import bench
+
+    data = {}
+    if os.path.exists(out):
+        with open(out) as f:
+            data = json.load(f)
+    rd, wr = _num("dram__bytes_read.sum"), _num("dram__bytes_write.sum")
+    data[key] = {"dram_bytes_per_ray" if "ray" in key else "dram_bytes_per_unit": (rd + wr) / n_units, "dram_bytes_read": rd, "dram_bytes_write": wr,
+                 "units": n_units, "kernel": vals[hdr.index("Kernel Name")], "source": "ncu --set full capture " + os.path.basename(rep),
+                 "kernel_source_hash": bench.kernel_source_hash()}
+    with open(out, "w") as f:
+        json.dump(data, f, indent=1)
+    print("wrote", out, data[key])

@@ -75,10 +75,49 @@ def main():
                     assert (np.abs(got - ref).max(axis=2) > 1e-6).mean() < 1e-3, f"root={root} closest {name}"
             assert cam.filter_stats()["samples"] == hi - lo  # (a rank whose slice holds no highlight has 0 splats)
             assert cam.filter_stats()["crypto_dropped"] == 0
+    # ---- the scalable combine: round-robin tiles of source samples, reduce-scatter, per-rank resolve, gather -------------
+    aovs2 = [("RGBA", 0, 1), ("light0", 0, 0), ("light1", 0, 0), ("N", 1, 0)]
+
+    def run2(c, k):
+        fr = workloads.highlight_frame(W, H, spp, c.state.tan_fov, dev, n_extra_aov=2, samples=k)
+        c.filter_begin(W, H, aovs2)
+        # closest AOVs need globally unique sample indices: the position of the rank's first sample in the concatenation of all shares
+        c.filter_accumulate(fr["px"], fr["py"], fr["rgba"], fr["pos_cs"], 1.0 / spp, aov_values=[None, fr["aov_values"][0], fr["aov_values"][1], fr["rgba"]])
+        return fr
+
+    shares = [workloads.tile_partition(W, H, spp, r, world, tile=32, device=dev) for r in range(world)]
+    base = sum(int(s.numel()) for s in shares[:rank])
+    fr2 = workloads.highlight_frame(W, H, spp, cam.state.tan_fov, dev, n_extra_aov=2, samples=shares[rank])
+    cam.filter_begin(W, H, aovs2)
+    cam.filter_set_sample_base(base)
+    cam.filter_accumulate(fr2["px"], fr2["py"], fr2["rgba"], fr2["pos_cs"], 1.0 / spp, aov_values=[None, fr2["aov_values"][0], fr2["aov_values"][1], fr2["rgba"]])
+    cam.filter_reduce_scatter()
+    lo_px, n_px = cam.filter_slab()
+    assert n_px > 0 and (rank > 0 or lo_px == 0)
+    try:
+        cam.resolve(0)
+        raise AssertionError("lb_imager_resolve must refuse after lb_filter_reduce_scatter")
+    except Exception as e:  # noqa: BLE001
+        assert "slab" in str(e)
+    for root in (0, -1):
+        imgs = [cam.resolve_gather(a, root=root) for a in range(len(aovs2))]
+        torch.cuda.synchronize()
+        if rank == 0 or root == -1:
+            single = Camera(p, device=local)
+            run2(single, torch.cat(shares))
+            for a, (name, flt, role) in enumerate(aovs2):
+                want = single.resolve(a).cpu().numpy()
+                got = imgs[a].cpu().numpy()
+                if flt == 0:
+                    np.testing.assert_allclose(got, want, rtol=1e-4, atol=2e-5, err_msg=f"resolve_gather root={root} {name}")
+                else:
+                    assert (np.abs(got - want).max(axis=2) > 1e-6).mean() < 1e-3, f"resolve_gather root={root} closest {name}"
+        else:
+            assert all(i is None for i in imgs)
     dist.barrier()
     cam.comm_destroy()
     if rank == 0:
-        print(f"multi_gpu_check ok: world={world}, {total} samples, reduce + all-reduce match the single-GPU framebuffers")
+        print(f"multi_gpu_check ok: world={world}, {total} samples, reduce + all-reduce + reduce-scatter/gather match the single-GPU framebuffers")
     dist.destroy_process_group()
 
 

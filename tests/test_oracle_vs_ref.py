@@ -424,3 +424,38 @@ def test_cryptomatte_render_region(libs):
         np.testing.assert_array_equal(to, tr)
         for box in (dict(), dict(x0=x0 + 8, y0=y0 + 4, w=20, h=10)):
             np.testing.assert_array_equal(o.resolve(a, fill=-7.0, **box).view(np.uint32), r.resolve(a, fill=-7.0, **box).view(np.uint32))
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(enable_skydome=1), dict(enable_bidir_transmission=1, enable_skydome=1),
+                                dict(camera_type=abi.LB_CAMERA_THINLENS, focal_length_lentil=50.0, enable_skydome=1)])
+def test_filter_sample_branches_and_camera_matrix(kw):
+    """Transmission, volume, lentil_bidir_ignore, skydome / lentil_raydir, small world-space P and a rotated + translated
+    camera (lentil_filter.cpp:115-164): reference vs oracle, identical framebuffers."""
+    from tests.util import branch_frame
+
+    p = po_params(fstop=1.4, focus_dist=35.0, bidir_sample_mult=6, **kw)
+    o, r = orc.OracleCamera(p), ref.RefCamera(p)
+    W, H, spp = 128, 72, 9
+    f = branch_frame(o.state.tan_fov, W, H, spp)
+    aovs = [("RGBA", 0, 1), ("lentil_debug", 0, 2)]
+    args = (f["px"], f["py"], f["rgba"], f["pos"], 1.0 / spp)
+    more = dict(raydir=f["raydir"], transmission=f["transmission"], flags=f["flags"], world_to_camera=f["world_to_camera"])
+    o.filter_begin(W, H, aovs)
+    o.filter_accumulate(*args, **more)
+    r.filter_begin(W, H, aovs, spp=spp)
+    r.filter_accumulate(*args, **more)
+    st = o.filter_stats()
+    m = f["masks"]
+    assert st["redistributed"] > 50 and st["passthrough"] > st["redistributed"]
+    # the skydome patch is redistributed only when enabled; the zero-raydir patch never is
+    n_sun = int(m["sun"].sum())
+    o2 = orc.OracleCamera(po_params(fstop=1.4, focus_dist=35.0, bidir_sample_mult=6, **{**kw, "enable_skydome": 0}))
+    o2.filter_begin(W, H, aovs)
+    o2.filter_accumulate(*args, **more)
+    assert st["redistributed"] - o2.filter_stats()["redistributed"] == (n_sun if kw.get("enable_skydome") else 0)
+    for a in range(len(aovs)):
+        bo, wo = o.buffers(a)
+        br, wr = r.buffers(a)
+        np.testing.assert_array_equal(bo, br, err_msg=f"buffer of {aovs[a][0]}")
+        np.testing.assert_array_equal(wo, wr)
+        np.testing.assert_array_equal(o.resolve(a), r.resolve(a))

@@ -56,3 +56,23 @@ def test_highlight_frame_layout():
     assert torch.all(fr["pos_cs"][~hit, 3] == 1.0e30) and torch.all(fr["pos_cs"][hit, 2] == -75.0)
     total = sum(fr["aov_values"])
     assert torch.equal(total, fr["rgba"])  # the per-light AOVs partition the beauty
+
+
+def test_tile_partition_covers_every_sample_once_and_balances():
+    import torch
+
+    W, H, spp = 200, 120, 3
+    for world in (1, 2, 3, 8):
+        parts = [workloads.tile_partition(W, H, spp, r, world, tile=16) for r in range(world)]
+        allk = torch.cat(parts)
+        assert allk.numel() == W * H * spp and torch.equal(torch.sort(allk).values, torch.arange(W * H * spp))
+        sizes = [p.numel() for p in parts]
+        assert max(sizes) - min(sizes) <= 0.35 * (W * H * spp / world) + 16 * 16 * spp
+        for p in parts:  # the spp samples of a pixel are adjacent
+            assert torch.equal(p.reshape(-1, spp) // spp, (p.reshape(-1, spp)[:, :1] // spp).expand(-1, spp))
+    # a frame built from a partition holds exactly the samples of the range-built frame
+    k = workloads.tile_partition(64, 36, 4, 1, 2, tile=16)
+    a = workloads.highlight_frame(64, 36, 4, 0.36, "cpu", samples=k)
+    b = workloads.highlight_frame(64, 36, 4, 0.36, "cpu")
+    for key in ("px", "py", "rgba", "pos_cs"):
+        assert torch.equal(a[key], b[key][k])
