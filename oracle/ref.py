@@ -27,6 +27,40 @@ def available() -> bool:
     return os.path.exists(LIB_PATH)
 
 
+def _declare_scenario_api(L):
+    """argtypes of the entry points both builds of ref_harness.cpp export (the reference's nodes / the adaptor's nodes)"""
+    vp = C.c_void_p
+    L.ref_camera_create.argtypes = [C.POINTER(abi.CameraParams), C.POINTER(abi.BokehImage), C.POINTER(vp)]
+    L.ref_camera_destroy.argtypes = [vp]
+    L.ref_camera_get_state.argtypes = [vp, C.POINTER(abi.CameraState)]
+    L.ref_camera_set_state.argtypes = [vp, C.c_double, C.c_double]
+    L.ref_camera_set_pupil_geometry.argtypes = [vp, C.c_int, C.c_int]
+    L.ref_camera_create_rays.argtypes = [vp, C.c_size_t, C.c_uint64, C.POINTER(abi.RayIn), C.POINTER(abi.RayOut), C.c_int]
+    L.ref_filter_begin.argtypes = [vp, C.POINTER(abi.FrameDesc), C.c_int, C.POINTER(abi.AovDesc), C.c_int]
+    L.ref_filter_accumulate.argtypes = [vp, C.POINTER(abi.Samples), C.c_int]
+    L.ref_imager_resolve.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]
+    L.ref_filter_buffers.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(vp)]
+    L.ref_filter_crypto.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp]
+    return L
+
+
+ADAPTOR_LIB_PATH = os.path.join(os.path.dirname(HERE), "adaptor", "_build", "libadaptor.so")
+_ADAPTOR = None
+
+
+def adaptor_available() -> bool:
+    return os.path.exists(ADAPTOR_LIB_PATH)
+
+
+def adaptor_lib():
+    """adaptor/_build/libadaptor.so: the same harness (ref_harness.cpp -DLB_ADAPTOR) over the adaptor's Arnold nodes, which call
+    liblentil_b200.so -- needs a GPU."""
+    global _ADAPTOR
+    if _ADAPTOR is None:
+        _ADAPTOR = _declare_scenario_api(C.CDLL(ADAPTOR_LIB_PATH))
+    return _ADAPTOR
+
+
 def lib():
     global _LIB
     if _LIB is None:
@@ -69,30 +103,32 @@ def lib():
 class RefCamera(orc.OracleCamera):
     """struct Camera of the reference + its camera/filter/imager node callbacks."""
 
+    _L = staticmethod(lambda: lib())
+
     def __init__(self, params: abi.CameraParams, bokeh: np.ndarray | None = None):
         self._h = C.c_void_p()
         img, self._keep = orc.bokeh_image(bokeh)
-        rc = lib().ref_camera_create(C.byref(params), C.byref(img) if img is not None else None, C.byref(self._h))
+        rc = self._L().ref_camera_create(C.byref(params), C.byref(img) if img is not None else None, C.byref(self._h))
         if rc != 0:
             raise RuntimeError(f"ref_camera_create failed: {rc}")
         self.params = params
 
     def close(self):
         if self._h:
-            lib().ref_camera_destroy(self._h)
+            self._L().ref_camera_destroy(self._h)
             self._h = C.c_void_p()
 
     @property
     def state(self) -> abi.CameraState:
         s = abi.CameraState()
-        lib().ref_camera_get_state(self._h, C.byref(s))
+        self._L().ref_camera_get_state(self._h, C.byref(s))
         return s
 
     def set_state(self, aperture_radius, sensor_shift):
-        lib().ref_camera_set_state(self._h, aperture_radius, sensor_shift)
+        self._L().ref_camera_set_state(self._h, aperture_radius, sensor_shift)
 
     def set_pupil_geometry(self, outer: int, inner: int = 0):
-        lib().ref_camera_set_pupil_geometry(self._h, outer, inner)
+        self._L().ref_camera_set_pupil_geometry(self._h, outer, inner)
 
     def create_rays(self, sx, sy, dsx, dsy, lensx, lensy, ray_id_base: int = 0, nthreads: int = 1):
         n = sx.shape[0]
@@ -101,7 +137,7 @@ class RefCamera(orc.OracleCamera):
         out = {k: np.zeros((3, n), np.float32) for k in orc.RAY_OUT_FIELDS}
         out["tries"] = np.zeros(n, np.int32)
         rout = abi.RayOut(*[orc._ptr(out[k]) for k in orc.RAY_OUT_FIELDS], orc._ptr(out["tries"]))
-        rc = lib().ref_camera_create_rays(self._h, n, ray_id_base, C.byref(rin), C.byref(rout), nthreads)
+        rc = self._L().ref_camera_create_rays(self._h, n, ray_id_base, C.byref(rin), C.byref(rout), nthreads)
         assert rc == 0, rc
         return out
 
@@ -118,13 +154,13 @@ class RefCamera(orc.OracleCamera):
             arr[i].filter = flt
             arr[i].role = role
         self._naov = len(aovs)
-        rc = lib().ref_filter_begin(self._h, C.byref(self._frame), len(aovs), arr, aa)
+        rc = self._L().ref_filter_begin(self._h, C.byref(self._frame), len(aovs), arr, aa)
         assert rc == 0, rc
 
     def filter_accumulate(self, px, py, rgba, pos_cs, inv_density, aov_values=None, raydir=None, transmission=None, flags=None, nthreads=1, crypto=None,
                           world_to_camera=None):
         S, _keep = abi.host_samples(self._naov, px, py, rgba, pos_cs, inv_density, aov_values, raydir, transmission, flags, crypto, world_to_camera)
-        rc = lib().ref_filter_accumulate(self._h, C.byref(S), nthreads)
+        rc = self._L().ref_filter_accumulate(self._h, C.byref(S), nthreads)
         assert rc == 0, rc
 
     def filter_stats(self):
@@ -137,7 +173,7 @@ class RefCamera(orc.OracleCamera):
         w = f.xres if w is None else w
         h = f.yres if h is None else h
         out = np.full((h, w, 4), fill, np.float32)
-        rc = lib().ref_imager_resolve(self._h, aov, x0, y0, w, h, orc._ptr(out))
+        rc = self._L().ref_imager_resolve(self._h, aov, x0, y0, w, h, orc._ptr(out))
         assert rc == 0, rc
         return out
 
@@ -146,15 +182,21 @@ class RefCamera(orc.OracleCamera):
         ids = np.zeros((f.yres, f.xres, slots), np.float32)
         wts = np.zeros((f.yres, f.xres, slots), np.float32)
         tot = np.zeros((f.yres, f.xres), np.float32)
-        mx = lib().ref_filter_crypto(self._h, aov, slots, orc._ptr(ids), orc._ptr(wts), orc._ptr(tot))
+        mx = self._L().ref_filter_crypto(self._h, aov, slots, orc._ptr(ids), orc._ptr(wts), orc._ptr(tot))
         assert mx >= 0, mx
         return ids, wts, tot, mx
 
     def buffers(self, aov):
         b, w = C.c_void_p(), C.c_void_p()
-        rc = lib().ref_filter_buffers(self._h, aov, C.byref(b), C.byref(w))
+        rc = self._L().ref_filter_buffers(self._h, aov, C.byref(b), C.byref(w))
         assert rc == 0, rc
         f = self._frame
         buf = np.ctypeslib.as_array(C.cast(b, C.POINTER(C.c_float)), shape=(f.yres, f.xres, 4)).copy()
         wgt = np.ctypeslib.as_array(C.cast(w, C.POINTER(C.c_float)), shape=(f.yres, f.xres)).copy()
         return buf, wgt
+
+
+class AdaptorCamera(RefCamera):
+    """The adaptor's Arnold nodes (adaptor/lentil_b200_*.cpp over liblentil_b200.so) behind the same harness entry points."""
+
+    _L = staticmethod(lambda: adaptor_lib())

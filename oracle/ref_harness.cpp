@@ -16,11 +16,21 @@
 #include <thread>
 
 #include "../include/lentil_b200.h"
+#ifdef LB_ADAPTOR
+// Built a second time by adaptor/Makefile with -DLB_ADAPTOR: the SAME scenario code (universe, nodes, parameters, operator
+// AOV list, per-sample CreateRay, per-pixel FilterPixel, per-bucket DriverProcessBucket) then drives the node tables of the
+// adaptor (adaptor/lentil_b200_*.cpp over liblentil_b200.so) instead of the reference's.  Only the accessors that reach
+// into the reference's `struct Camera` differ: they go through the C ABI.
+#include "../CryptomatteArnold/cryptomatte/cryptomatte.h"
+#include "lentil_b200_adaptor.h"
+typedef LbAdaptorCamera Camera;
+#else
 // The three lens_* wrappers (lentil.h:1257-1313) sit behind `private:`; this test harness calls them
 // directly to pin the oracle's restatement of the generated bodies.  Layout is unaffected.
 #define private public
 #include "lentil.h"
 #undef private
+#endif
 
 extern const AtNodeMethods *lentilMethods;         // lentil_camera.cpp:5
 extern const AtNodeMethods *LentilFilterDataMtd;   // lentil_filter.cpp:6
@@ -36,6 +46,9 @@ struct ref_camera {
   std::vector<lb_aov_desc> aovs;
   lb_frame_desc frame{};
   int aa = 3;
+#ifdef LB_ADAPTOR
+  std::vector<float> host_buffer, host_weight;  // lb_filter_buffers_host copies handed out by ref_filter_buffers
+#endif
 };
 
 namespace {
@@ -166,6 +179,9 @@ void ref_camera_destroy(ref_camera *r) {
 }
 
 int ref_camera_get_state(const ref_camera *r, lb_camera_state *s) {
+#ifdef LB_ADAPTOR
+  return lb_camera_get_state(r->cam->cam, s);
+#else
   const Camera *c = r->cam;
   memset(s, 0, sizeof *s);
   s->aperture_radius = c->aperture_radius; s->sensor_shift = c->sensor_shift; s->tan_fov = c->tan_fov;
@@ -179,17 +195,26 @@ int ref_camera_get_state(const ref_camera *r, lb_camera_state *s) {
   s->lens_field_of_view = c->lens_field_of_view; s->lens_fstop = c->lens_fstop;
   s->lens_aperture_radius_at_fstop = c->lens_aperture_radius_at_fstop;
   return LB_OK;
+#endif
 }
 int ref_camera_set_pupil_geometry(ref_camera *r, int outer, int inner) {
+#ifdef LB_ADAPTOR
+  return lb_camera_set_pupil_geometry(r->cam->cam, outer, inner);
+#else
   const char *names[3] = {"spherical", "cyl-y", "cyl-x"};
   r->cam->lens_outer_pupil_geometry = names[outer];
   r->cam->lens_inner_pupil_geometry = names[inner];
   return LB_OK;
+#endif
 }
 int ref_camera_set_state(ref_camera *r, double aperture_radius, double sensor_shift) {
+#ifdef LB_ADAPTOR
+  return lb_camera_set_state(r->cam->cam, aperture_radius, sensor_shift);
+#else
   r->cam->aperture_radius = aperture_radius;
   r->cam->sensor_shift = sensor_shift;
   return LB_OK;
+#endif
 }
 
 // camera_create_ray per sample.  nthreads > 1 calls it concurrently on the shared Camera the way Arnold's
@@ -197,6 +222,13 @@ int ref_camera_set_state(ref_camera *r, double aperture_radius, double sensor_sh
 int ref_camera_create_rays(ref_camera *r, size_t n, uint64_t, const lb_ray_in *in, const lb_ray_out *out, int nthreads) {
   shim_default_universe() = &r->uni;
   float *dst[7] = {out->origin, out->dir, out->dOdx, out->dOdy, out->dDdx, out->dDdy, out->weight};
+#ifdef LB_ADAPTOR
+  {  // what a host that knows its upcoming camera samples does at bucket entry; CreateRay below is per sample as ever
+    std::vector<AtCameraInput> all(n);
+    for (size_t i = 0; i < n; ++i) all[i] = AtCameraInput{in->sx[i], in->sy[i], in->dsx[i], in->dsy[i], in->lensx[i], in->lensy[i], 0.f};
+    if (!getenv("LB_ADAPTOR_NO_PREFETCH") && lentil_b200_prefetch_rays(&r->camera, n, all.data()) != LB_OK) return LB_ERR_CUDA;
+  }
+#endif
   auto work = [&](size_t lo, size_t hi) {
     for (size_t i = lo; i < hi; ++i) {
       AtCameraInput ci{in->sx[i], in->sy[i], in->dsx[i], in->dsy[i], in->lensx[i], in->lensy[i], 0.f};
@@ -289,6 +321,9 @@ int ref_filter_accumulate(ref_camera *r, const lb_samples *S, int nthreads) {
     for (int t = 0; t < nthreads; ++t) th.emplace_back(work, runs.size() * t / nthreads, runs.size() * (t + 1) / nthreads);
     for (auto &t : th) t.join();
   }
+#ifdef LB_ADAPTOR
+  lentil_b200_flush(&r->camera);  // the threads' partial batches (the imager flushes them as well)
+#endif
   return r->cam->redistribution ? LB_OK : LB_ERR_STATE;
 }
 
@@ -300,6 +335,52 @@ int ref_imager_resolve(ref_camera *r, int aov, int x0, int y0, int w, int h, flo
   return LB_OK;
 }
 
+#ifdef LB_ADAPTOR
+int ref_filter_buffers(ref_camera *r, int aov, float **buffer, float **weight) {
+  const int a = (aov >= 0 && aov < (int)r->aovs.size()) ? lentil_b200_aov_index(&r->camera, r->aovs[aov].name) : -1;
+  if (a < 0) return LB_ERR_INVALID;
+  lentil_b200_flush(&r->camera);
+  const size_t npx = (size_t)r->frame.xres * r->frame.yres;
+  r->host_buffer.resize(npx * 4);
+  r->host_weight.resize(npx);
+  const int rc = lb_filter_buffers_host(r->cam->cam, a, r->host_buffer.data(), r->host_weight.data());
+  if (buffer) *buffer = r->host_buffer.data();
+  if (weight) *weight = r->host_weight.data();
+  return rc;
+}
+// AOVData::crypto_hash_map as the reference harness dumps it: ids ascending (std::map order), free slots NaN
+int ref_filter_crypto(ref_camera *r, int aov, int slots, float *ids_out, float *weights_out, float *total_out) {
+  const int a = (aov >= 0 && aov < (int)r->aovs.size()) ? lentil_b200_aov_index(&r->camera, r->aovs[aov].name) : -1;
+  if (a < 0) return -1;
+  lentil_b200_flush(&r->camera);
+  int k = 0;
+  if (lb_filter_crypto_host(r->cam->cam, a, nullptr, nullptr, &k) != LB_OK) return -1;
+  const size_t npx = (size_t)r->frame.xres * r->frame.yres;
+  std::vector<float> ids(npx * k), wts(npx * k), plane(npx * 4);
+  if (lb_filter_crypto_host(r->cam->cam, a, ids.data(), wts.data(), nullptr) != LB_OK) return -1;
+  if (lb_filter_buffers_host(r->cam->cam, a, plane.data(), nullptr) != LB_OK) return -1;
+  size_t mx = 0;
+  for (size_t p = 0; p < npx; ++p) {
+    std::vector<std::pair<float, float>> e;
+    for (int j = 0; j < k; ++j) {
+      uint32_t bits;
+      memcpy(&bits, &ids[p * k + j], 4);
+      if (bits != 0xFFFFFFFFu) e.push_back({ids[p * k + j], wts[p * k + j]});
+    }
+    std::sort(e.begin(), e.end(), [](const std::pair<float, float> &x, const std::pair<float, float> &y) { return x.first < y.first; });
+    mx = std::max(mx, e.size());
+    if (total_out) total_out[p] = plane[4 * p];
+    for (int j = 0; j < slots; ++j) {
+      const bool on = j < (int)e.size();
+      const uint32_t nanbits = 0xFFFFFFFFu;
+      if (ids_out) { if (on) ids_out[p * slots + j] = e[j].first; else memcpy(&ids_out[p * slots + j], &nanbits, 4); }
+      if (weights_out) weights_out[p * slots + j] = on ? e[j].second : 0.0f;
+    }
+  }
+  return (int)mx;
+}
+}  // extern "C"
+#else
 static AOVData *find_aov(ref_camera *r, int aov) {
   if (aov < 0 || aov >= (int)r->aovs.size()) return nullptr;
   for (auto &a : r->cam->aovs) if (a.name == AtString(r->aovs[aov].name)) return &a;
@@ -414,3 +495,4 @@ int ref_trace_ray_bw_po(ref_camera *r, const double target[3], int px, int py, i
 float ref_get_coc_thinlens(ref_camera *r, float z) { return r->cam->get_coc_thinlens(AtVector(0.f, 0.f, z)); }
 
 }  // extern "C"
+#endif  // LB_ADAPTOR

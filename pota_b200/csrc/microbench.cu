@@ -123,7 +123,7 @@ __global__ void k_debug_primitives(size_t n, const uint32_t *__restrict__ v0, co
     lcg_float_out[4 * i + k] = lb::lcg_rng(s);
     lcg_state_out[4 * i + k] = s;
   }
-  const float x = (lcg_float_out[4 * i] - 0.5f) * 20.0f;  // fast_sin / fast_cos argument in [-10, 10)
+  const float x = __fmul_rn(__fsub_rn(lcg_float_out[4 * i], 0.5f), 20.0f);  // fast_sin / fast_cos argument in [-10, 10), no FMA contraction
   trig_out[2 * i] = lb::fast_sin(x);
   trig_out[2 * i + 1] = lb::fast_cos(x);
 }
