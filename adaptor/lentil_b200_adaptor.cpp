@@ -2,6 +2,7 @@
 #include "lentil_b200_adaptor.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 
 void LbSampleBatch::clear() {
@@ -12,14 +13,17 @@ void LbSampleBatch::clear() {
   n = 0;
 }
 
+static std::atomic<uint64_t> g_next_uid{1};
+LbAdaptorCamera::LbAdaptorCamera() : uid(g_next_uid.fetch_add(1)) {}
+
 LbAdaptorCamera::~LbAdaptorCamera() {
   for (LbSampleBatch *b : batches) delete b;
   if (cam) lb_camera_destroy(cam);
 }
 
 LbSampleBatch &lb_adaptor_thread_batch(LbAdaptorCamera *c) {
-  thread_local std::unordered_map<LbAdaptorCamera *, LbSampleBatch *> mine;
-  LbSampleBatch *&b = mine[c];
+  thread_local std::unordered_map<uint64_t, LbSampleBatch *> mine;  // batches are owned (and freed) by their camera
+  LbSampleBatch *&b = mine[c->uid];
   if (!b) {
     b = new LbSampleBatch();
     std::lock_guard<std::mutex> lk(c->mu);

@@ -39,6 +39,8 @@ struct LbSampleBatch {
 };
 
 struct LbAdaptorCamera {
+  const uint64_t uid;  // threads key their batch by this, not by the address (a later camera may reuse it)
+  LbAdaptorCamera();
   lb_camera *cam = nullptr;
   lb_camera_params params{};
   AtNode *camera_node = nullptr, *options_node = nullptr;

@@ -19,7 +19,7 @@ keeps: `roofline.splat_*` (device-resident value, executed FMA-slot fraction, re
 
 N > 1: one process per GPU.  Camera rays shard with no collective (every rank traces its own frame's
 worth of samples, weak scaling).  The splat frame is ONE frame for all ranks (strong scaling): source
-samples are dealt to the ranks in round-robin 64x64 pixel tiles, every rank accumulates a full-frame
+samples are dealt to the ranks in round-robin 4x4 pixel tiles, every rank accumulates a full-frame
 partial, lb_filter_reduce_scatter (one ncclReduceScatter per plane over NVLink) leaves every rank owning a
 pixel slab, which it resolves itself; lb_imager_resolve_gather collects the slabs on rank 0.
 """
@@ -48,7 +48,7 @@ CHUNK_RAYS = FRAME_W * FRAME_H * 4  # 33 177 600 rays per call on the e2e path (
 IN_KEYS = ("sx", "sy", "dsx", "dsy", "lensx", "lensy")
 CPU_SAMPLE_PER_THREAD = 200_000  # rays per host thread in the CPU legs (~1-2 s with the compiled reference)
 CPU_SPLAT_SOURCES_PER_THREAD = 100  # redistributed source samples per host thread in the CPU splat leg (2000 splats each, ~10 s in all)
-SPLAT_TILE = 64  # round-robin tile edge of the multi-GPU source-sample partition
+SPLAT_TILE = 4  # round-robin tile edge (pixels) of the multi-GPU source-sample partition: a highlight of ~10 px is shared by several ranks
 
 
 def camera_params():

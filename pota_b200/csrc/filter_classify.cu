@@ -176,7 +176,7 @@ k_filter_classify(const __grid_constant__ FilterConsts fc, const __grid_constant
   const unsigned mask = __ballot_sync(0xffffffffu, redistribute);
   unsigned base = 0;
   if (lane == 0 && mask) {
-    base = atomicAdd(&counters->work_count, (unsigned)__popc(mask));
+    base = atomicAdd(&aovs.work_heads[0], (unsigned)__popc(mask));
     atomicAdd(&counters->redistributed, (unsigned long long)__popc(mask));
   }
   base = __shfl_sync(0xffffffffu, base, 0);

@@ -41,32 +41,47 @@ struct FilterState {
   size_t block_floats = 0;
   unsigned long long *zkey = nullptr, *zkey_debug = nullptr;
   size_t zkey_npx = 0;     // pixels the two key planes are allocated for
-  // Every operation that touches the framebuffers waits for `ev_done` on its stream and records it again when it
-  // has issued its work: accumulates, reduces and resolves issued on DIFFERENT streams execute in call order (they
-  // share the work list, the counters and the planes).
+  // Ordering across streams.  `ev_done` is recorded by every begin / reduce / resolve (operations that need the planes
+  // complete or exclusive); an accumulate waits for it and for the previous user of its scratch slot, and records the slot's
+  // event; begin / reduce / resolve wait for `ev_done` and for every slot (wait_all_accumulates).  So accumulates overlap
+  // each other, everything else executes in call order.  Frames with closest-filter AOVs use one slot (their gather step
+  // must see the batches in order).
   cudaEvent_t ev_done = nullptr;
   bool scattered = false;  // lb_filter_reduce_scatter has run: this rank's planes are complete only inside its slab
   float4 *gather = nullptr;  // [npx_pad] resolved pixels of one AOV (lb_imager_resolve_gather)
   bool has_closest = false, has_debug_closest = false;
-  WorkItem *work = nullptr;
-  size_t work_cap = 0;
-  uint16_t *debug_samples = nullptr;
+  // Batch scratch (work list, its two heads, per-sample helper arrays).  A pool, so that accumulates issued on different
+  // streams -- the chunks of lb_filter_accumulate_host, the flushes of several render threads -- run CONCURRENTLY: their
+  // framebuffer updates are atomic and commute, and a persistent splat kernel whose work list is running dry leaves SM
+  // slots to the next batch's kernel instead of idling them.
+  struct Scratch {
+    WorkItem *work = nullptr;
+    size_t work_cap = 0;
+    uint16_t *debug_samples = nullptr;
+    float2 *crypto_cache = nullptr;   // [n_crypto][work_cap][crypto_cache_stride]
+    int crypto_cache_stride = 0;
+    unsigned int *heads = nullptr;    // [2]
+    cudaEvent_t done = nullptr;       // recorded after the last kernel that used this scratch
+  };
+  static constexpr int kScratch = 4;
+  Scratch scratch[kScratch];
+  int next_scratch = 0;
+  cudaEvent_t ev_accum = nullptr;     // scratch for "wait for every accumulate in flight"
   // cryptomatte: per crypto AOV one table of [npx][crypto_slots] id bits followed by [npx][crypto_slots] weights
   int n_crypto = 0, crypto_slots = 0;
   int crypto_of[kMaxAov]{};          // AOV index -> crypto table index, -1 for the others
   int crypto_rank[kMaxAov]{};        // 0 / 2 / 4 from the AOV name (lentil_imager.cpp:124-126)
   uint32_t *crypto_tables = nullptr; // n_crypto tables back to back
   size_t crypto_table_words = 0;     // 2 * npx * crypto_slots
-  float2 *crypto_cache = nullptr;    // batch scratch [n_crypto][work_cap][crypto_cache_stride]
-  int crypto_cache_stride = 0;
   FilterCounters *d_counters = nullptr;
   uint64_t sample_base = 0;
   uint64_t samples_seen = 0;  // source samples handed to accumulate since lb_filter_begin
   // host-path staging: two device blocks so that the copy of chunk k+1 overlaps the kernels of chunk k
-  char *stage[2] = {nullptr, nullptr};
+  char *stage[3] = {nullptr, nullptr, nullptr};
   size_t stage_bytes = 0;
-  cudaEvent_t stage_ready[2] = {nullptr, nullptr}, stage_free[2] = {nullptr, nullptr};
+  cudaEvent_t stage_ready[3] = {nullptr, nullptr, nullptr}, stage_free[3] = {nullptr, nullptr, nullptr};
   cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaStream_t work_stream[3] = {nullptr, nullptr, nullptr};  // lb_filter_accumulate_host: chunk k runs on work_stream[k % 3]
   // lb_imager_resolve_host: the whole region of an AOV is resolved once into pinned host memory, buckets are served from it
   float4 *res_dev = nullptr;           // [npx]
   uint8_t *brk_dev = nullptr;          // [npx] cryptomatte: pixel holds <= rank ids (ends a bucket row, lentil_imager.cpp:132-134)
@@ -164,7 +179,7 @@ void fill_consts(lb_camera *c, const FilterState *f, FilterConsts &fc) {
   fc.aspect_full = (double)f->frame.xres_without_region / (double)f->frame.yres_without_region;
 }
 
-void fill_aovs(const FilterState *f, AovSet &A, const lb_samples *S) {
+void fill_aovs(const FilterState *f, AovSet &A, const lb_samples *S, const FilterState::Scratch *sc) {
   memset(&A, 0, sizeof A);
   const float *const *values = S ? S->aov_values : nullptr;
   A.crypto_slots = f->crypto_slots;
@@ -180,26 +195,41 @@ void fill_aovs(const FilterState *f, AovSet &A, const lb_samples *S) {
       A.crypto_key[a] = f->crypto_tables + (size_t)t * f->crypto_table_words;
       A.crypto_wgt[a] = (float *)(A.crypto_key[a] + f->crypto_table_words / 2);
       A.crypto_ids[a] = (S && S->crypto_depth > 0 && S->crypto_ids) ? S->crypto_ids[a] : nullptr;
-      A.crypto_cache[a] = f->crypto_cache ? f->crypto_cache + (size_t)t * f->work_cap * f->crypto_cache_stride : nullptr;
+      A.crypto_cache[a] = (sc && sc->crypto_cache) ? sc->crypto_cache + (size_t)t * sc->work_cap * sc->crypto_cache_stride : nullptr;
     }
   }
   A.weight = f->block + (size_t)f->n_aov * f->npx_pad * 4;
   A.zkey = f->zkey;
   A.zkey_debug = f->zkey_debug;
-  A.debug_samples = f->has_debug_closest ? f->debug_samples : nullptr;
+  A.debug_samples = (f->has_debug_closest && sc) ? sc->debug_samples : nullptr;
+  A.work_heads = sc ? sc->heads : nullptr;
 }
 
-int ensure_batch_capacity(FilterState *f, size_t n, int crypto_depth) {
+int ensure_batch_capacity(FilterState *f, FilterState::Scratch *sc, size_t n, int crypto_depth) {
   const int stride = f->n_crypto ? std::max(crypto_depth, 1) : 0;
-  if (f->work_cap >= n && f->crypto_cache_stride >= stride) return LB_OK;
-  n = std::max(n, f->work_cap);
-  cudaFree(f->work); cudaFree(f->debug_samples); cudaFree(f->crypto_cache);
-  f->work = nullptr; f->debug_samples = nullptr; f->crypto_cache = nullptr; f->work_cap = 0; f->crypto_cache_stride = 0;
-  CUF(cudaMalloc(&f->work, n * sizeof(WorkItem)));
-  CUF(cudaMalloc(&f->debug_samples, n * sizeof(uint16_t)));
-  if (stride) CUF(cudaMalloc(&f->crypto_cache, (size_t)f->n_crypto * n * stride * sizeof(float2)));
-  f->work_cap = n;
-  f->crypto_cache_stride = stride;
+  if (!sc->heads) CUF(cudaMalloc(&sc->heads, 2 * sizeof(unsigned)));
+  if (!sc->done) {
+    CUF(cudaEventCreateWithFlags(&sc->done, cudaEventDisableTiming));
+    CUF(cudaEventRecord(sc->done, f->stream));
+  }
+  if (sc->work_cap >= n && sc->crypto_cache_stride >= stride) return LB_OK;
+  n = std::max(n, sc->work_cap);
+  CUF(cudaEventSynchronize(sc->done));  // the previous user of this slot
+  cudaFree(sc->work); cudaFree(sc->debug_samples); cudaFree(sc->crypto_cache);
+  sc->work = nullptr; sc->debug_samples = nullptr; sc->crypto_cache = nullptr; sc->work_cap = 0; sc->crypto_cache_stride = 0;
+  CUF(cudaMalloc(&sc->work, n * sizeof(WorkItem)));
+  CUF(cudaMalloc(&sc->debug_samples, n * sizeof(uint16_t)));
+  if (stride) CUF(cudaMalloc(&sc->crypto_cache, (size_t)f->n_crypto * n * stride * sizeof(float2)));
+  sc->work_cap = n;
+  sc->crypto_cache_stride = stride;
+  return LB_OK;
+}
+
+// begin / reduce / resolve: after every accumulate in flight and after the previous operation of that kind
+int wait_all_accumulates(FilterState *f, cudaStream_t stream) {
+  CUF(cudaStreamWaitEvent(stream, f->ev_done, 0));
+  for (auto &sc : f->scratch)
+    if (sc.done) CUF(cudaStreamWaitEvent(stream, sc.done, 0));
   return LB_OK;
 }
 
@@ -208,30 +238,34 @@ int accumulate_device(lb_camera *c, FilterState *f, const lb_samples *S, cudaStr
   if (S->n == 0) return LB_OK;
   if (S->n > 0xFFFFFFFFull) return lb_fail(LB_ERR_INVALID, "batch larger than 2^32 samples");
   if (S->crypto_depth < 0 || S->crypto_depth > LB_CRYPTO_MAX_DEPTH) return lb_fail(LB_ERR_INVALID, "crypto_depth outside [0, LB_CRYPTO_MAX_DEPTH]");
-  int rc = ensure_batch_capacity(f, S->n, S->crypto_depth);
+  // closest-filter AOVs fetch the winning sample's value per batch (launch_closest_gather): batches in order, one slot
+  FilterState::Scratch *sc = &f->scratch[(f->has_closest || f->has_debug_closest) ? 0 : f->next_scratch];
+  f->next_scratch = (f->next_scratch + 1) % FilterState::kScratch;
+  int rc = ensure_batch_capacity(f, sc, S->n, S->crypto_depth);
   if (rc != LB_OK) return rc;
   FilterConsts fc;
   fill_consts(c, f, fc);
   AovSet A;
-  fill_aovs(f, A, S);
+  fill_aovs(f, A, S, sc);
   SampleIO io{S->n, S->px, S->py, (const float4 *)S->rgba, (const float4 *)S->pos_cs, (const float4 *)S->raydir,
               (const float4 *)S->transmission, S->flags, S->inv_density,
               f->n_crypto && S->crypto_depth > 0 ? S->crypto_count : nullptr, f->n_crypto && S->crypto_depth > 0 ? S->crypto_opacity : nullptr};
   // AiWorldToCameraMatrix of the batch (lentil_filter.cpp:139-142); identity when the caller hands camera-space positions
   for (int r = 0; r < 4; ++r)
     for (int k = 0; k < 3; ++k) io.w2c[r][k] = S->world_to_camera ? S->world_to_camera[4 * r + k] : (r == k ? 1.0f : 0.0f);
-  CUF(cudaStreamWaitEvent(stream, f->ev_done, 0));  // the batch scratch and the planes are shared with the previous call
+  CUF(cudaStreamWaitEvent(stream, f->ev_done, 0));  // the last begin / reduce / resolve
+  CUF(cudaStreamWaitEvent(stream, sc->done, 0));    // the previous batch that used this scratch slot
   f->scattered = false;
   for (int a = 0; a < f->n_aov; ++a) f->res_valid[a] = false;
-  CUF(cudaMemsetAsync(&f->d_counters->work_count, 0, 2 * sizeof(unsigned), stream));
-  CUF(launch_filter_classify(fc, A, io, f->work, f->d_counters, f->sample_base, stream));
+  CUF(cudaMemsetAsync(sc->heads, 0, 2 * sizeof(unsigned), stream));
+  CUF(launch_filter_classify(fc, A, io, sc->work, f->d_counters, f->sample_base, stream));
   if (cam_params(c).camera_type == LB_CAMERA_THINLENS)
-    CUF(launch_filter_splat_thinlens(cam_consts(c), cam_thin(c), fc, A, io, f->work, f->d_counters, f->sample_base, cam_num_sms(c), stream));
+    CUF(launch_filter_splat_thinlens(cam_consts(c), cam_thin(c), fc, A, io, sc->work, f->d_counters, f->sample_base, cam_num_sms(c), stream));
   else
-    CUF(launch_filter_splat(cam_lens_kernel(c), cam_lens(c), cam_consts(c), fc, A, io, f->work, f->d_counters, f->sample_base,
+    CUF(launch_filter_splat(cam_lens_kernel(c), cam_lens(c), cam_consts(c), fc, A, io, sc->work, f->d_counters, f->sample_base,
                             cam_num_sms(c), stream));
   if (f->has_closest || f->has_debug_closest) CUF(launch_closest_gather(fc, A, io, f->sample_base, stream));
-  CUF(cudaEventRecord(f->ev_done, stream));
+  CUF(cudaEventRecord(sc->done, stream));
   f->sample_base += S->n;
   f->samples_seen += S->n;
   return LB_OK;
@@ -249,13 +283,19 @@ __global__ void k_mask_closest(const unsigned long long *__restrict__ local_key,
 void filter_state_destroy(FilterState *f) {
   if (!f) return;
   if (f->comm) { if (NcclApi *n = load_nccl()) n->CommDestroy(f->comm); }
-  cudaFree(f->block); cudaFree(f->zkey); cudaFree(f->zkey_debug); cudaFree(f->work); cudaFree(f->debug_samples);
-  cudaFree(f->crypto_tables); cudaFree(f->crypto_cache);
-  cudaFree(f->d_counters); cudaFree(f->stage[0]); cudaFree(f->stage[1]); cudaFree(f->gather); cudaFree(f->res_dev); cudaFree(f->brk_dev);
+  cudaFree(f->block); cudaFree(f->zkey); cudaFree(f->zkey_debug);
+  for (auto &sc : f->scratch) {
+    cudaFree(sc.work); cudaFree(sc.debug_samples); cudaFree(sc.crypto_cache); cudaFree(sc.heads);
+    if (sc.done) cudaEventDestroy(sc.done);
+  }
+  cudaFree(f->crypto_tables);
+  cudaFree(f->d_counters); cudaFree(f->gather); cudaFree(f->res_dev); cudaFree(f->brk_dev);
   for (int a = 0; a < kMaxAov; ++a) { cudaFreeHost(f->res_host[a]); cudaFreeHost(f->brk_host[a]); }
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < 3; ++i) {
+    cudaFree(f->stage[i]);
     if (f->stage_ready[i]) cudaEventDestroy(f->stage_ready[i]);
     if (f->stage_free[i]) cudaEventDestroy(f->stage_free[i]);
+    if (f->work_stream[i]) cudaStreamDestroy(f->work_stream[i]);
   }
   if (f->ev_done) cudaEventDestroy(f->ev_done);
   if (f->stream) cudaStreamDestroy(f->stream);
@@ -320,8 +360,14 @@ int lb_filter_begin(lb_camera *c, const lb_frame_desc *frame, int n_aov, const l
   if (n_crypto && slots > LB_CRYPTO_MAX_SLOTS) return lb_fail(LB_ERR_INVALID, "crypto_slots above LB_CRYPTO_MAX_SLOTS");
   const size_t table_words = n_crypto ? 2 * npx * (size_t)slots : 0;
   if (n_crypto != f->n_crypto || table_words != f->crypto_table_words) {
-    cudaFree(f->crypto_tables); cudaFree(f->crypto_cache);
-    f->crypto_tables = nullptr; f->crypto_cache = nullptr; f->crypto_cache_stride = 0;
+    cudaFree(f->crypto_tables);  // (waits for work in flight)
+    f->crypto_tables = nullptr;
+    for (auto &sc : f->scratch) {  // the per-batch caches are sized by the number of cryptomatte AOVs: reallocated on next use
+      cudaFree(sc.work); cudaFree(sc.debug_samples); cudaFree(sc.crypto_cache);
+      sc.work = nullptr; sc.debug_samples = nullptr; sc.crypto_cache = nullptr;
+      sc.work_cap = 0;
+      sc.crypto_cache_stride = 0;
+    }
     f->n_crypto = 0; f->crypto_table_words = 0;
     if (n_crypto) CUF(cudaMalloc(&f->crypto_tables, (size_t)n_crypto * table_words * 4));
     f->n_crypto = n_crypto;
@@ -332,7 +378,7 @@ int lb_filter_begin(lb_camera *c, const lb_frame_desc *frame, int n_aov, const l
   // zero everything on the filter's stream, ordered after whatever still reads the previous frame; the first
   // accumulate waits for `ev_done` on its own stream
   cudaStream_t st = f->stream;
-  CUF(cudaStreamWaitEvent(st, f->ev_done, 0));
+  { const int rcw = wait_all_accumulates(f, st); if (rcw != LB_OK) return rcw; }
   for (int t = 0; t < n_crypto; ++t) {
     uint32_t *tab = f->crypto_tables + (size_t)t * table_words;
     CUF(cudaMemsetAsync(tab, 0xFF, table_words / 2 * 4, st));               // ids: kCryptoFree
@@ -369,9 +415,11 @@ int lb_filter_accumulate(lb_camera *c, const lb_samples *S, lb_stream stream) {
   return accumulate_device(c, f, S, (cudaStream_t)stream);
 }
 
-// Host-buffer variant: samples are staged to the device in chunks through TWO staging blocks: the copies of chunk k+1
-// (copy stream) overlap the classify / splat kernels of chunk k (filter stream).  Source memory may be pageable
-// (Arnold's sample buffers are): the driver then stages the copy itself, still beside the kernels.
+// Host-buffer variant: samples are staged to the device in chunks through THREE staging blocks.  Chunk k is copied on the
+// copy stream and classified + splatted on work_stream[k % 3] with its own batch scratch, so the copy of chunk k+1 overlaps
+// the kernels of chunk k AND the kernels of consecutive chunks overlap each other: a chunk holds only the highlights of its
+// part of the frame, its persistent splat kernel runs dry early and the next chunk's kernel takes over the free SM slots.
+// Source memory may be pageable (Arnold's sample buffers are): the driver then stages the copy itself, still beside the kernels.
 int lb_filter_accumulate_host(lb_camera *c, const lb_samples *S) {
   if (!c || !S) return lb_fail(LB_ERR_INVALID, "null argument");
   FilterState *f = cam_filter(c);
@@ -381,6 +429,7 @@ int lb_filter_accumulate_host(lb_camera *c, const lb_samples *S) {
   if (S->n == 0) return LB_OK;
   std::lock_guard<std::mutex> lk(cam_mutex(c));
   DeviceGuard g(cam_device(c));
+  constexpr int kSlots = 3;
   const size_t chunk = std::min<size_t>(S->n, (size_t)1 << 21);
   int n_val = 0;
   for (int a = 0; a < f->n_aov; ++a) if (S->aov_values && S->aov_values[a]) ++n_val;
@@ -392,21 +441,22 @@ int lb_filter_accumulate_host(lb_camera *c, const lb_samples *S) {
                      (Dn ? 1 + 4 * Dn * (1 + (size_t)n_ids) : 0);
   const size_t need = per * chunk + 256 * (16 + 2 * kMaxAov);
   if (f->stage_bytes < need) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kSlots; ++i) {
       cudaFree(f->stage[i]); f->stage[i] = nullptr;
       if (!f->stage_ready[i]) CUF(cudaEventCreateWithFlags(&f->stage_ready[i], cudaEventDisableTiming));
       if (!f->stage_free[i]) CUF(cudaEventCreateWithFlags(&f->stage_free[i], cudaEventDisableTiming));
+      if (!f->work_stream[i]) CUF(cudaStreamCreateWithFlags(&f->work_stream[i], cudaStreamNonBlocking));
     }
     f->stage_bytes = 0;
-    for (int i = 0; i < 2; ++i) CUF(cudaMalloc(&f->stage[i], need));
+    for (int i = 0; i < kSlots; ++i) CUF(cudaMalloc(&f->stage[i], need));
     f->stage_bytes = need;
   }
   int rc = LB_OK;
   size_t k = 0;
   for (size_t base = 0; base < S->n && rc == LB_OK; base += chunk, ++k) {
-    const int slot = (int)(k & 1);
+    const int slot = (int)(k % kSlots);
     const size_t m = std::min(chunk, S->n - base);
-    if (k >= 2) CUF(cudaStreamWaitEvent(f->copy_stream, f->stage_free[slot], 0));  // the kernels of chunk k-2 have read this block
+    if (k >= (size_t)kSlots) CUF(cudaStreamWaitEvent(f->copy_stream, f->stage_free[slot], 0));  // the kernels of chunk k-3 have read this block
     char *p = f->stage[slot];
     auto put = [&](const void *src, size_t elem) -> void * {
       if (!src) return nullptr;
@@ -435,12 +485,13 @@ int lb_filter_accumulate_host(lb_camera *c, const lb_samples *S) {
       D.crypto_count = (const uint8_t *)put(S->crypto_count, 1);
     }
     CUF(cudaGetLastError());
+    cudaStream_t ws = f->work_stream[slot];
     CUF(cudaEventRecord(f->stage_ready[slot], f->copy_stream));
-    CUF(cudaStreamWaitEvent(f->stream, f->stage_ready[slot], 0));
-    rc = accumulate_device(c, f, &D, f->stream);
-    CUF(cudaEventRecord(f->stage_free[slot], f->stream));
+    CUF(cudaStreamWaitEvent(ws, f->stage_ready[slot], 0));
+    rc = accumulate_device(c, f, &D, ws);
+    CUF(cudaEventRecord(f->stage_free[slot], ws));
   }
-  CUF(cudaStreamSynchronize(f->stream));  // the caller may reuse its arrays and the result is complete on return
+  for (int i = 0; i < kSlots; ++i) CUF(cudaStreamSynchronize(f->work_stream[i]));  // the caller may reuse its arrays; the result is complete
   return rc;
 }
 
@@ -479,7 +530,7 @@ int lb_imager_resolve(lb_camera *c, int aov, int x0, int y0, int w, int h, float
   if (f->scattered) return lb_fail(LB_ERR_STATE, "after lb_filter_reduce_scatter a rank holds only its slab: use lb_imager_resolve_gather");
   DeviceGuard g(cam_device(c));
   cudaStream_t stream = (cudaStream_t)stream_;
-  CUF(cudaStreamWaitEvent(stream, f->ev_done, 0));
+  { const int rcw = wait_all_accumulates(f, stream); if (rcw != LB_OK) return rcw; }
   if (f->crypto_of[aov] >= 0) {
     const uint32_t *key = f->crypto_tables + (size_t)f->crypto_of[aov] * f->crypto_table_words;
     CUF(launch_resolve_crypto(key, (const float *)(key + f->crypto_table_words / 2), (const float4 *)(f->block + (size_t)aov * f->npx_pad * 4),
@@ -525,7 +576,7 @@ int lb_imager_resolve_host(lb_camera *c, int aov, int x0, int y0, int w, int h, 
     if (!f->res_host[aov]) CUF(cudaMallocHost(&f->res_host[aov], f->npx * sizeof(float4)));
     if (crypto && !f->brk_host[aov]) CUF(cudaMallocHost(&f->brk_host[aov], f->npx));
     cudaStream_t st = f->stream;
-    CUF(cudaStreamWaitEvent(st, f->ev_done, 0));
+    { const int rcw = wait_all_accumulates(f, st); if (rcw != LB_OK) return rcw; }
     const int xr = f->frame.xres, yr = f->frame.yres;
     if (crypto) {
       const uint32_t *key = f->crypto_tables + (size_t)f->crypto_of[aov] * f->crypto_table_words;
@@ -677,7 +728,7 @@ int lb_filter_reduce(lb_camera *c, int root, lb_stream stream_) {
   DeviceGuard g(cam_device(c));
   cudaStream_t stream = (cudaStream_t)stream_;
   auto check = [&](ncclResult_t r) { return r == ncclSuccess ? LB_OK : lb_fail(LB_ERR_COMM, n->GetErrorString ? n->GetErrorString(r) : "nccl error"); };
-  CUF(cudaStreamWaitEvent(stream, f->ev_done, 0));
+  { const int rcw = wait_all_accumulates(f, stream); if (rcw != LB_OK) return rcw; }
   for (int a = 0; a < f->n_aov; ++a) f->res_valid[a] = false;
   int rc = reduce_keys_and_tables(f, n, root, stream);
   if (rc != LB_OK) return rc;
@@ -703,7 +754,7 @@ int lb_filter_reduce_scatter(lb_camera *c, lb_stream stream_) {
   DeviceGuard g(cam_device(c));
   cudaStream_t stream = (cudaStream_t)stream_;
   auto check = [&](ncclResult_t r) { return r == ncclSuccess ? LB_OK : lb_fail(LB_ERR_COMM, n->GetErrorString ? n->GetErrorString(r) : "nccl error"); };
-  CUF(cudaStreamWaitEvent(stream, f->ev_done, 0));
+  { const int rcw = wait_all_accumulates(f, stream); if (rcw != LB_OK) return rcw; }
   for (int a = 0; a < f->n_aov; ++a) f->res_valid[a] = false;
   int rc = reduce_keys_and_tables(f, n, -1, stream);
   if (rc != LB_OK) return rc;
@@ -746,7 +797,7 @@ int lb_imager_resolve_gather(lb_camera *c, int aov, float *rgba_out, int root, l
   if (!single && !f->scattered) return lb_fail(LB_ERR_STATE, "lb_filter_reduce_scatter has not been called for this frame");
   const bool mine = single || root < 0 || root == f->rank;
   if (mine && !rgba_out) return lb_fail(LB_ERR_INVALID, "null output on a receiving rank");
-  CUF(cudaStreamWaitEvent(stream, f->ev_done, 0));
+  { const int rcw = wait_all_accumulates(f, stream); if (rcw != LB_OK) return rcw; }
   const float4 *plane = (const float4 *)(f->block + (size_t)aov * f->npx_pad * 4);
   const float *wplane = f->block + (size_t)f->n_aov * f->npx_pad * 4;
   if (single) {

@@ -200,19 +200,19 @@ LB_DEV void splat_work_item(const E &ev, const CamConsts<float> &cam, const Filt
   }
 }
 
-// (A variant with two attempt slots per lane and FFMA2/FMUL2 Newton bodies was built and measured in r01: correct, 20-30 %
-// fewer instructions, but 168 registers -> 12 warps/SM and 12 % slower than this kernel at 5 blocks/SM; see
-// profiles/r01_k2_packed_experiment.txt and the commit "Experiment: packed two-slot K2".)
+// (A variant with two attempt slots per lane and FFMA2/FMUL2 Newton bodies was built and measured in r01: correct, 20-30 % fewer
+// instructions, but 168 registers -> 12 warps/SM and 12 % slower; profiles/r01_k2_packed_experiment.txt.  Its successor is the
+// mirror-packed body of lensgen/emit_folded.py: packed over the lens symmetry instead of over two attempts, same register count.)
 
 // persistent kernel body: warps pull work items until the list is drained
 template <typename E>
 LB_DEV void splat_persistent(const E &ev, const CamConsts<float> &cam, const FilterConsts &fc, const AovSet &aovs, const SampleIO &s,
                              const WorkItem *__restrict__ work, FilterCounters *counters, uint64_t sample_base) {
   const int lane = threadIdx.x & 31;
-  const unsigned n_work = *((volatile unsigned *)&counters->work_count);
+  const unsigned n_work = *((volatile unsigned *)&aovs.work_heads[0]);
   for (;;) {
     unsigned idx = 0;
-    if (lane == 0) idx = atomicAdd(&counters->work_next, 1u);
+    if (lane == 0) idx = atomicAdd(&aovs.work_heads[1], 1u);
     idx = __shfl_sync(0xffffffffu, idx, 0);
     if (idx >= n_work) break;
     const WorkItem w = work[idx];

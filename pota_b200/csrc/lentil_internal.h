@@ -90,6 +90,7 @@ struct AovSet {
   float2 *crypto_cache[kMaxAov];     // this batch: [n][max(crypto_depth,1)] merged {id, weight} of each sample, packed,
                                      // kCryptoFree-terminated (cryptomatte_construct_cache, lentil.h:779-811)
   int32_t crypto_slots, crypto_depth;
+  unsigned int *work_heads;          // this batch's work list: [0] items appended by classify, [1] next item handed to a warp
 };
 constexpr uint32_t kCryptoFree = 0xFFFFFFFFu;  // a NaN bit pattern: Cryptomatte hashes are never NaN
 constexpr int kCryptoMaxDepth = 8;
@@ -112,11 +113,10 @@ struct WorkItem {  // one redistributed source sample
   float csp[3];        // camera-space position after unit scaling / skydome substitution (lentil_filter.cpp:121-148)
 };
 
-struct FilterCounters {  // device-side mirror of lb_filter_stats + work queue heads
+struct FilterCounters {  // device-side mirror of lb_filter_stats
   unsigned long long samples, redistributed, splats, attempts, passthrough;
   unsigned long long newton_its;
   unsigned long long crypto_dropped;
-  unsigned int work_count, work_next;
 };
 
 cudaError_t launch_filter_classify(const FilterConsts &fc, const AovSet &aovs, const SampleIO &s, WorkItem *work,

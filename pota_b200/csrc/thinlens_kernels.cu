@@ -267,10 +267,10 @@ k_filter_splat_thinlens(const __grid_constant__ CamConsts<float> cam, const __gr
                         const __grid_constant__ AovSet aovs, const __grid_constant__ SampleIO s, const WorkItem *__restrict__ work,
                         FilterCounters *__restrict__ counters, uint64_t sample_base) {
   const int lane = threadIdx.x & 31;
-  const unsigned n_work = *((volatile unsigned *)&counters->work_count);
+  const unsigned n_work = *((volatile unsigned *)&aovs.work_heads[0]);
   for (;;) {
     unsigned idx = 0;
-    if (lane == 0) idx = atomicAdd(&counters->work_next, 1u);
+    if (lane == 0) idx = atomicAdd(&aovs.work_heads[1], 1u);
     idx = __shfl_sync(0xffffffffu, idx, 0);
     if (idx >= n_work) break;
     const WorkItem w = work[idx];

@@ -228,7 +228,7 @@ def lens_unit(lens) -> tuple[str, dict]:
     dap = [d("ap_x", 2), d("ap_x", 3), d("ap_y", 2), d("ap_y", 3)]
     dout = [d("out_dx", 0), d("out_dx", 1), d("out_dy", 0), d("out_dy", 1)]
     src = ["// generated by pota_b200.lensgen.emit_cuda from pota_b200/lenses/%s.json -- do not edit" % lens["lens_id"],
-           '#include "../camera_kernels.cuh"', '#include "../filter_kernels%s.cuh"' % ("_packed" if K2_PACKED else ""), '#include "../unrolled_dispatch.h"', "",
+           '#include "../camera_kernels.cuh"', '#include "../filter_kernels.cuh"', '#include "../unrolled_dispatch.h"', "",
            "namespace lb {", "namespace {", "", "struct Eval%d {  // 5-variate bodies (wavelength as a variable)" % k]
     stats = {}
     # op statistics of the first-generation K1 bodies (kept for the comparison in tests / DESIGN; not emitted any more)
@@ -245,19 +245,13 @@ def lens_unit(lens) -> tuple[str, dict]:
                                  ["ap[0]", "ap[1]", "J[0]", "J[1]", "J[2]", "J[3]", "out[0]", "out[1]", "out[2]", "out[3]", "K[0]", "K[1]", "K[2]", "K[3]"])
     src += body
     stats["lt_all"] = (mul, ffma)
-    if K2_PACKED:  # experimental two-slot kernel (csrc/filter_kernels_packed.cuh)
-        body, _, _ = emit_group("lt_all2", "const float2 b[5], float2 ap[2], float2 J[4], float2 out[4], float2 K[4]",
-                                [P["ap_x"], P["ap_y"]] + dap + [P["out_x"], P["out_y"], P["out_dx"], P["out_dy"]] + dout,
-                                ["ap[0]", "ap[1]", "J[0]", "J[1]", "J[2]", "J[3]", "out[0]", "out[1]", "out[2]", "out[3]", "K[0]", "K[1]", "K[2]", "K[3]"],
-                                packed=True, acc=PACKED_ACC)
-        src += body
     src += ["};", ""]
     # second generation: wavelength folded into the coefficients (emit_folded.py); K1 two-ray packed, K2 mirror packed
     for imm in (None, emit_folded.LAMBDA_550):
         fsrc, fstats, _, _ = emit_folded.folded_evaluators(lens, imm_lambda=imm)
         src += fsrc
         stats.update({g: (v if isinstance(v, tuple) else (v["fmul"] + v["fmul2"], v["ffma"] + v["ffma2"])) for g, v in fstats.items()})
-    splat = "splat_persistent%s" % ("2" if K2_PACKED else "")
+    splat = "splat_persistent"
     k1_sig = "(const __grid_constant__ CamConsts<float> cam, const __grid_constant__ RayIO io, size_t n, uint64_t ray_id_base"
     k2_sig = ("(const __grid_constant__ CamConsts<float> cam, const __grid_constant__ FilterConsts fc, const __grid_constant__ AovSet aovs,\n"
               "    const __grid_constant__ SampleIO s, const WorkItem *__restrict__ work, FilterCounters *__restrict__ counters, uint64_t sample_base")
@@ -313,8 +307,6 @@ K1_MIN_BLOCKS = ", " + os.environ.get("LB_K1_MINBLOCKS", "4")
 K2_MIN_BLOCKS = ", " + os.environ.get("LB_K2_MINBLOCKS", "5")
 K1F_MIN_BLOCKS = ", " + os.environ.get("LB_K1F_MINBLOCKS", "4")
 K2F_MIN_BLOCKS = ", " + os.environ.get("LB_K2F_MINBLOCKS", "5")
-K2_PACKED = os.environ.get("LB_K2_PACKED", "0") == "1"  # experimental, see csrc/filter_kernels_packed.cuh
-PACKED_ACC = int(os.environ.get("LB_PACKED_ACC", "2"))  # accumulators per long polynomial of lt_all2 (register pressure knob)
 
 
 def emit_cuda(out_dir: str, only=None):

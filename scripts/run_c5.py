@@ -1,5 +1,7 @@
 """Config C5 (BASELINE.json configs[4]): 7680x4320 multi-AOV redistribution (beauty + 8 per-light RGBA AOVs + a
-closest-filter AOV), source samples partitioned by range over the ranks, NCCL framebuffer reduce, resolve on rank 0.
+closest-filter AOV).  Source samples are dealt to the ranks in round-robin pixel tiles; every rank accumulates full-frame
+partials; the combine is either lb_filter_reduce_scatter + per-rank resolve + gather on rank 0 (default) or the round-1
+path lb_filter_reduce to rank 0 + resolve there (--combine reduce), so both can be measured on the same box.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29513 scripts/run_c5.py [--spp 16]
     python scripts/run_c5.py --spp 4          (single GPU)
@@ -23,6 +25,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--spp", type=int, default=16)
     ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--combine", default="scatter", choices=["scatter", "reduce"])
+    ap.add_argument("--tile", type=int, default=16)
     a = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -32,8 +36,14 @@ def main():
     p = abi.CameraParams.defaults(camera_type=1, lens_model=5, fstop=1.4, focus_dist=35.0, bidir_sample_mult=10, bokeh_enable_image=1)
     cam = Camera(p, bokeh=workloads.disc_bokeh_image(250), device=local)
     aovs = [("RGBA", 0, 1)] + [(f"light{k}", 0, 0) for k in range(8)] + [("N", 1, 0)]
-    total = W * H * a.spp
-    lo, hi = total * rank // world, total * (rank + 1) // world
+    mine = workloads.tile_partition(W, H, a.spp, rank, world, tile=a.tile, device=dev)  # int64 sample indices of this rank
+    n_mine = int(mine.numel())
+    sizes = torch.zeros(world, dtype=torch.int64, device=dev)
+    sizes[rank] = n_mine
+    if world > 1:
+        dist.all_reduce(sizes)
+    base = int(sizes[:rank].sum().item())  # globally unique sample indices for the closest-filter AOV
+    lo, hi = 0, n_mine
     cam.filter_begin(W, H, aovs)
     if world > 1:
         uid = [Camera.comm_unique_id() if rank == 0 else None]
@@ -44,11 +54,11 @@ def main():
     times = []
     for step in range(a.steps + 1):
         cam.filter_begin(W, H, aovs)
-        cam.filter_set_sample_base(lo)
+        cam.filter_set_sample_base(base)
         t_acc = t_red = 0.0
         for c0 in range(lo, hi, chunk):
             m = min(chunk, hi - c0)
-            fr = workloads.highlight_frame(W, H, a.spp, cam.state.tan_fov, dev, c0, m, grid=(8, 4), n_extra_aov=8)
+            fr = workloads.highlight_frame(W, H, a.spp, cam.state.tan_fov, dev, grid=(8, 4), n_extra_aov=8, samples=mine[c0:c0 + m])
             vals = [None] + fr["aov_values"] + [fr["aov_values"][0]]
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
@@ -61,9 +71,15 @@ def main():
         if world > 1:
             dist.barrier()
         e0.record(stream)
-        cam.filter_reduce(root=0, stream=stream)
-        e1.record(stream)
-        imgs = [cam.resolve(k, stream=stream) for k in range(len(aovs))] if rank == 0 else []
+        if a.combine == "scatter":
+            cam.filter_reduce_scatter(stream=stream)
+            e1.record(stream)
+            out = torch.empty((H, W, 4), dtype=torch.float32, device=dev) if rank == 0 else None
+            imgs = [cam.resolve_gather(k, root=0, stream=stream, out=out) for k in range(len(aovs))]  # one reusable 531 MB image
+        else:
+            cam.filter_reduce(root=0, stream=stream)
+            e1.record(stream)
+            imgs = [cam.resolve(k, stream=stream) for k in range(len(aovs))] if rank == 0 else []
         e2.record(stream)
         torch.cuda.synchronize()
         t_red, t_res = e0.elapsed_time(e1), e1.elapsed_time(e2)
@@ -81,8 +97,9 @@ def main():
         splats = float(tsum[3])
         total_ms = float(tmax[0] + tmax[1] + tmax[2])
         block_gb = W * H * (4 * len(aovs) + 1) * 4 / 1e9
-        print(json.dumps({"config": f"C5 {W}x{H}x{a.spp}spp, {len(aovs)} AOVs (9 gaussian RGBA + 1 closest), {world} GPU(s)", "accumulate_ms": float(tmax[0]),
-                          "reduce_ms": float(tmax[1]), "resolve_ms": float(tmax[2]), "splats": splats, "splats_per_s": splats / (total_ms * 1e-3),
+        print("C5 " + json.dumps({"config": f"C5 {W}x{H}x{a.spp}spp, {len(aovs)} AOVs (9 gaussian RGBA + 1 closest), {world} GPU(s)", "combine": a.combine,
+                          "partition": f"round-robin {a.tile}x{a.tile} pixel tiles", "accumulate_ms": float(tmax[0]),
+                          "reduce_ms": float(tmax[1]), "resolve_gather_ms": float(tmax[2]), "splats": splats, "splats_per_s": splats / (total_ms * 1e-3),
                           "framebuffer_block_GB": block_gb, "reduce_GBps_per_rank": block_gb / (float(tmax[1]) * 1e-3) if world > 1 else None}))
     if world > 1:
         dist.destroy_process_group()
