@@ -199,8 +199,8 @@ void fill_aovs(const FilterState *f, AovSet &A, const lb_samples *S, const Filte
     }
   }
   A.weight = f->block + (size_t)f->n_aov * f->npx_pad * 4;
-  A.zkey = f->zkey;
-  A.zkey_debug = f->zkey_debug;
+  A.zkey = f->has_closest ? f->zkey : nullptr;  // planes that are not in use are not zeroed either
+  A.zkey_debug = f->has_debug_closest ? f->zkey_debug : nullptr;
   A.debug_samples = (f->has_debug_closest && sc) ? sc->debug_samples : nullptr;
   A.work_heads = sc ? sc->heads : nullptr;
 }

@@ -19,15 +19,15 @@ __global__ void k_closest_gather(const __grid_constant__ FilterConsts fc, const 
                                  const __grid_constant__ SampleIO s, uint64_t sample_base) {
   const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= (size_t)fc.xres * fc.yres) return;
-  const unsigned long long key = aovs.zkey[p];
+  const unsigned long long key = aovs.zkey ? aovs.zkey[p] : ~0ull;
   if (key != ~0ull) {
     const uint32_t idx = (0xFFFFFFFFu - (uint32_t)key) - (uint32_t)sample_base;
     if ((size_t)idx < s.n)
       for (int a = 0; a < fc.n_aov; ++a)
         if (aovs.filter[a] == 1 && aovs.role[a] != 2) aovs.buffer[a][p] = aov_value(aovs, s, a, idx, 0.f);
   }
-  const unsigned long long dkey = aovs.zkey_debug[p];
-  if (dkey != ~0ull && aovs.debug_samples) {
+  const unsigned long long dkey = (aovs.zkey_debug && aovs.debug_samples) ? aovs.zkey_debug[p] : ~0ull;
+  if (dkey != ~0ull) {
     const uint32_t idx = (0xFFFFFFFFu - (uint32_t)dkey) - (uint32_t)sample_base;
     if ((size_t)idx < s.n)
       for (int a = 0; a < fc.n_aov; ++a)

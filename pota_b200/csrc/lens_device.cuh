@@ -121,35 +121,19 @@ LB_DEV int upper_bound_f(const float *__restrict__ a, int n, float v) {
   }
   return lo;
 }
-// The same upper_bound in TWO rounds of independent loads instead of log2(n) dependent ones: `coarse` holds the last entry of
-// every block of 16 (built on the host).  For a non-decreasing table the predicate !(v < a[i]) holds on a prefix, so counting
-// it equals the binary search's result exactly.  The thin-lens splat kernel was latency-bound on the 2 x 8 dependent loads of
-// the two searches (ncu r02: long_scoreboard the top stall, 31 % of the stall samples on the search's compare).
-LB_DEV int upper_bound_blocked(const float *__restrict__ a, const float *__restrict__ coarse, int n, float v) {
-  const int nb = (n + 15) >> 4;
-  int kb = 0;
-#pragma unroll 8
-  for (int i = 0; i < nb; ++i) kb += !(v < __ldg(coarse + i));
-  if (kb >= nb) return n;
-  const int lo = kb << 4;
-  int cnt = 0;
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const int j = lo + i;
-    cnt += (j < n) && !(v < __ldg(a + (j < n ? j : n - 1)));
-  }
-  return lo + cnt;
-}
+// (r02, measured and withdrawn: the same upper_bound as two rounds of 16 independent loads over host-built coarse tables.  The
+// thin-lens splat kernel stalls on the searches' dependent loads, but it is the L1's wavefront rate that bounds it -- every lane
+// reads another row of the column table, 32 wavefronts per load instruction -- and 64 loads per attempt instead of 16 took the
+// kernel from 3.4 ms to 8.8 ms on the C3 frame.  profiles/r02_thinlens_splat_ncu.txt)
 template <typename T, typename C>
 LB_DEV void bokeh_sample(const C &cam, float randomNumberRow, float randomNumberColumn, T &lx, T &ly) {
   const int n = cam.bokeh_n;
-  const int nb = (n + 15) >> 4;
-  int r = upper_bound_blocked(cam.cdf_row, cam.cdf_row_coarse, n, randomNumberRow);
+  int r = upper_bound_f(cam.cdf_row, n, randomNumberRow);
   if (r >= n) r = n - 1;
   const int actualPixelRow = __ldg(cam.row_idx + r);
   const int recalulatedPixelRow = actualPixelRow - ((n - 1) / 2);
   const int startPixel = actualPixelRow * n;
-  int c = startPixel + upper_bound_blocked(cam.cdf_col + startPixel, cam.cdf_col_coarse + actualPixelRow * nb, n, randomNumberColumn);
+  int c = startPixel + upper_bound_f(cam.cdf_col + startPixel, n, randomNumberColumn);
   if (c >= startPixel + n) c = startPixel + n - 1;
   const int actualPixelColumn = __ldg(cam.col_idx + c);
   const int relativePixelColumn = actualPixelColumn - startPixel;

@@ -56,8 +56,6 @@ struct CamConsts {
   const int32_t *row_idx;
   const float *cdf_col;
   const int32_t *col_idx;
-  const float *cdf_row_coarse;  // last entry of every block of 16 of cdf_row / of each row of cdf_col (upper_bound_blocked)
-  const float *cdf_col_coarse;  // [bokeh_n][ceil(bokeh_n / 16)]
   T inv_outer_R, abs_inv_outer_R, outer_R2;  // 1/R, 1/|R|, R^2 of the outer pupil sphere (lt_iterate_tail_sphere)
   double lambda_exact;    // wavelength in double: the host folds it into the polynomial coefficients (gen/, EvalFA / EvalFB)
 };

@@ -187,7 +187,7 @@ struct lb_camera {
   ThinConsts thin{};
   CamConsts<double> camd{};
   // bokeh CDF on device
-  float *d_cdf_row = nullptr, *d_cdf_col = nullptr;  // d_cdf_row: [n] cdf_row, then [nb] its coarse table, then [n][nb] the coarse table of cdf_col
+  float *d_cdf_row = nullptr, *d_cdf_col = nullptr;
   int32_t *d_row_idx = nullptr, *d_col_idx = nullptr;
   int bokeh_n = 0;
   // host-path pipeline
@@ -237,9 +237,6 @@ void refresh_consts(lb_camera *c) {
     k.outer_geom = s.outer_pupil_geometry;
     k.inner_geom = s.inner_pupil_geometry;
     k.cdf_row = c->d_cdf_row; k.row_idx = c->d_row_idx; k.cdf_col = c->d_cdf_col; k.col_idx = c->d_col_idx;
-    const size_t bn = (size_t)c->bokeh_n, bnb = (bn + 15) / 16;
-    k.cdf_row_coarse = c->d_cdf_row ? c->d_cdf_row + bn : nullptr;
-    k.cdf_col_coarse = c->d_cdf_row ? c->d_cdf_row + bn + bnb : nullptr;
   };
   fill(c->camf);
   fill(c->camd);
@@ -345,16 +342,9 @@ int camera_setup_impl(lb_camera *c, const lb_camera_params *p, const lb_bokeh_im
     BokehTables bt;
     if (!bt.build(bokeh)) return fail(LB_ERR_IMAGE, "bokeh image missing, not square or < 3 channels");
     const size_t n = bt.n, n2 = n * n;
-    // coarse tables of the blocked search (lens_device.cuh upper_bound_blocked): the last entry of every block of 16
-    const size_t nb = (n + 15) / 16;
-    std::vector<float> row_pack(n + nb + n * nb);
-    std::copy(bt.cdf_row.begin(), bt.cdf_row.end(), row_pack.begin());
-    for (size_t b = 0; b < nb; ++b) row_pack[n + b] = bt.cdf_row[std::min(16 * b + 15, n - 1)];
-    for (size_t r = 0; r < n; ++r)
-      for (size_t b = 0; b < nb; ++b) row_pack[n + nb + r * nb + b] = bt.cdf_col[r * n + std::min(16 * b + 15, n - 1)];
-    CU(cudaMalloc(&c->d_cdf_row, row_pack.size() * 4)); CU(cudaMalloc(&c->d_row_idx, n * 4));
+    CU(cudaMalloc(&c->d_cdf_row, n * 4)); CU(cudaMalloc(&c->d_row_idx, n * 4));
     CU(cudaMalloc(&c->d_cdf_col, n2 * 4)); CU(cudaMalloc(&c->d_col_idx, n2 * 4));
-    CU(cudaMemcpy(c->d_cdf_row, row_pack.data(), row_pack.size() * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->d_cdf_row, bt.cdf_row.data(), n * 4, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(c->d_row_idx, bt.row_idx.data(), n * 4, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(c->d_cdf_col, bt.cdf_col.data(), n2 * 4, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(c->d_col_idx, bt.col_idx.data(), n2 * 4, cudaMemcpyHostToDevice));

@@ -49,11 +49,17 @@ def test_camera_node_create_ray(ref, kw, monkeypatch):
     ins = workloads.camera_samples(w, -(-n // w), 1, "cpu", 0, n, "linear")
     arrs = [ins[k].numpy() for k in IN_KEYS]
     want, got = r.create_rays(*arrs), a.create_rays(*arrs, nthreads=4)
-    np.testing.assert_array_equal(want["weight"] == 0, got["weight"] == 0)
-    live = want["weight"][0] != 0
+    # rays whose first try succeeds (the reference's retries draw their lens samples from its process-global xor128, the one
+    # stated deviation; `tries` is not observable through the reference's interface, the oracle reports it)
+    from oracle import orc
+
+    first = orc.OracleCamera(p, img).create_rays(*arrs, nthreads=4)["tries"] == 0
+    assert first.mean() > 0.2
+    np.testing.assert_array_equal(want["weight"][:, first], got["weight"][:, first])
+    live = first & (want["weight"][0] != 0)
     for k in ("origin", "dir"):
         e = rel_err_vec(got[k][:, live], want[k][:, live])
-        assert (e <= 1e-4).mean() >= 0.9995, (k, float(e.max()))  # the reference's retries draw from its global xor128: a few rays differ
+        assert (e <= 1e-4).mean() >= 0.9999, (k, float(e.max()))
     # without the per-bucket prefetch every CreateRay is a one-ray GPU call: same answers
     monkeypatch.setenv("LB_ADAPTOR_NO_PREFETCH", "1")
     slow = a.create_rays(*[x[:200] for x in arrs])
