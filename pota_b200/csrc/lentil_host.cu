@@ -361,6 +361,7 @@ int camera_setup_impl(lb_camera *c, const lb_camera_params *p, const lb_bokeh_im
       const int maxrays = 1000;
       DevBuf<double4> out;
       CU(out.alloc(maxrays));
+      CU(cudaMemset(out.p, 0, maxrays * sizeof(double4)));  // entry 0 is not a ray (the loop of lentil.h:1395 starts at 1)
       CU(launch_fstop_rays(c->lens, c->camd, maxrays, s.lens_outer_pupil_radius, out.p, nullptr));
       std::vector<double4> h(maxrays);
       CU(cudaMemcpy(h.data(), out.p, maxrays * sizeof(double4), cudaMemcpyDeviceToHost));

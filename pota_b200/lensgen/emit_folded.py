@@ -504,12 +504,14 @@ def folded_evaluators(lens, imm_lambda=None):
     sfx = "_folded" if imm_lambda is None else "_imm"
     # ---- K1 ----
     ca = Coefs()
-    body_ap, mul, ffma = emit_group_folded("ap_jac2", "const float2 b[5], float2 ap[2], float2 J[4]", [P["ap_x"], P["ap_y"]] + dap,
-                                           ["ap[0]", "ap[1]", "J[0]", "J[1]", "J[2]", "J[3]"], ca, imm_lambda=imm_lambda)
+    group = emit_group_horner if POLY_FORM == "horner" else emit_group_folded
+    mirror_group = emit_mirror_group_horner if POLY_FORM == "horner" else emit_mirror_group
+    body_ap, mul, ffma = group("ap_jac2", "const float2 b[5], float2 ap[2], float2 J[4]", [P["ap_x"], P["ap_y"]] + dap,
+                               ["ap[0]", "ap[1]", "J[0]", "J[1]", "J[2]", "J[3]"], ca, imm_lambda=imm_lambda)
     stats["ap_jac2" + sfx] = (mul, ffma)
-    body_o5, mul, ffma = emit_group_folded("out5_2", "const float2 b[5], float2 out[4], float2 &T",
-                                           [P["out_x"], P["out_y"], P["out_dx"], P["out_dy"], P["out_t"]],
-                                           ["out[0]", "out[1]", "out[2]", "out[3]", "T"], ca, imm_lambda=imm_lambda)
+    body_o5, mul, ffma = group("out5_2", "const float2 b[5], float2 out[4], float2 &T",
+                               [P["out_x"], P["out_y"], P["out_dx"], P["out_dy"], P["out_t"]],
+                               ["out[0]", "out[1]", "out[2]", "out[3]", "T"], ca, imm_lambda=imm_lambda)
     stats["out5_2" + sfx] = (mul, ffma)
     if imm_lambda is None:
         src += host_fold_code("a%d" % k, ca, "FoldA%d" % k)
@@ -522,11 +524,11 @@ def folded_evaluators(lens, imm_lambda=None):
     pairs = [(P["ap_x"], P["ap_y"], "ap[0]", "ap[1]"), (dap[0], dap[3], "J[0]", "J[3]"), (dap[1], dap[2], "J[1]", "J[2]"),
              (P["out_x"], P["out_y"], "out[0]", "out[1]"), (P["out_dx"], P["out_dy"], "out[2]", "out[3]"),
              (dout[0], dout[3], "K[0]", "K[3]"), (dout[1], dout[2], "K[1]", "K[2]")]
-    body_lt, st = emit_mirror_group("lt_all", "const float b[5], float ap[2], float J[4], float out[4], float K[4]", pairs, cb,
-                                    imm_lambda=imm_lambda)
+    body_lt, st = mirror_group("lt_all", "const float b[5], float ap[2], float J[4], float out[4], float K[4]", pairs, cb,
+                               imm_lambda=imm_lambda)
     stats["lt_all_mirror" + ("" if imm_lambda is None else "_imm")] = st
-    body_t, mul, ffma = emit_group_folded("transmittance_", "const float b[5], float &T", [P["out_t"]], ["T"], cb, packed=False,
-                                          imm_lambda=imm_lambda)
+    body_t, mul, ffma = group("transmittance_", "const float b[5], float &T", [P["out_t"]], ["T"], cb, packed=False,
+                              imm_lambda=imm_lambda)
     stats["transmittance" + sfx] = (mul, ffma)
     if imm_lambda is None:
         src += host_fold_code("b%d" % k, cb, "FoldB%d" % k)
@@ -582,3 +584,209 @@ def host_test_source(lens_indices, imm_lambda=None):
             "int ft_out5_2(int lens, double lambda, const float2 *b, float2 *out) {", "  switch (lens) {"] + cases_o5 + ["  }", "  return -1;", "}",
             "}"]
     return "\n".join(src) + "\n"
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Horner form (r02b).  The bodies above form every distinct monomial of a polynomial GROUP once (a shared multiplication
+# DAG) and then spend one FMA per term: ~1.65 FMA-pipe operations per term on the pack.  A greedy multivariate Horner scheme
+# per polynomial -- pick the variable most terms contain, P = v^k * A + B, recurse -- needs no monomials at all: every step
+# is ONE fused multiply-add, ~1.3 operations per term (profiles/r02_poly_opcounts.txt), at shorter live ranges.  The mirror
+# packing of K2 carries over unchanged: with the packed variables {x, y}, {y, x}, {dx, dy}, {dy, dx} the scheme of P evaluates
+# its mirror partner Q in the other half, provided their supports mirror each other (checked per pair; pairs that do not
+# are evaluated as two scalar schemes).
+# ---------------------------------------------------------------------------------------------------------
+import os as _os
+
+POLY_FORM = _os.environ.get("LB_POLY_FORM", "horner")  # horner | dag
+
+
+def _horner_cost(exps):
+    """operation count of the greedy scheme for a list of exponent tuples (no code emitted)"""
+    if not exps:
+        return 0
+    if len(exps) == 1:
+        return sum(1 for e in exps[0] if e > 0)
+    v = max(range(4), key=lambda i: sum(1 for t in exps if t[i] > 0))
+    with_v = [t for t in exps if t[v] > 0]
+    rest = [t for t in exps if t[v] == 0]
+    k = min(t[v] for t in with_v)
+    a = [tuple(e - (k if i == v else 0) for i, e in enumerate(t)) for t in with_v]
+    ca = 0 if (len(a) == 1 and sum(a[0]) == 0) else _horner_cost(a)
+    return ca + _horner_cost(rest) + 1
+
+
+class HornerEmitter:
+    """Emits one polynomial as a nested Horner scheme.  packed: float2 arithmetic on FFMA2/FMUL2."""
+
+    def __init__(self, lines, packed, var_expr, power_expr, coef_expr, prefix, stats):
+        self.lines, self.packed, self.var_expr, self.power_expr, self.coef_expr = lines, packed, var_expr, power_expr, coef_expr
+        self.prefix, self.stats, self.n = prefix, stats, 0
+
+    def _tmp(self):
+        self.n += 1
+        return "%s%d" % (self.prefix, self.n)
+
+    def _mul(self, a, b):
+        t = self._tmp()
+        if self.packed:
+            self.lines.append("    const float2 %s = __fmul2_rn(%s, %s);" % (t, a, b))
+            self.stats["fmul2"] += 1
+        else:
+            self.lines.append("    const float %s = %s * %s;" % (t, a, b))
+            self.stats["fmul"] += 1
+        return t
+
+    def _fma(self, a, b, c):
+        t = self._tmp()
+        if self.packed:
+            self.lines.append("    const float2 %s = __ffma2_rn(%s, %s, %s);" % (t, a, b, c))
+            self.stats["ffma2"] += 1
+        else:
+            self.lines.append("    const float %s = fmaf(%s, %s, %s);" % (t, a, b, c))
+            self.stats["ffma"] += 1
+        return t
+
+    def _pow(self, v, k):
+        return self.var_expr(v) if k == 1 else self.power_expr(v, k)
+
+    def emit(self, terms):
+        """terms: [(payload, exps)] -> expression holding the value (a temporary or a coefficient expression)"""
+        if len(terms) == 1:
+            c, e = terms[0]
+            expr = self.coef_expr(c)
+            for v in range(4):
+                if e[v] > 0:
+                    expr = self._mul(expr, self._pow(v, e[v]))
+            return expr
+        # the variable whose choice gives the cheapest scheme one level down (ties: most terms)
+        best = None
+        for v in range(4):
+            with_v = [t for t in terms if t[1][v] > 0]
+            if not with_v:
+                continue
+            rest = [t for t in terms if t[1][v] == 0]
+            k = min(t[1][v] for t in with_v)
+            a = [tuple(x - (k if i == v else 0) for i, x in enumerate(t[1])) for t in with_v]
+            cost = (0 if (len(a) == 1 and sum(a[0]) == 0) else _horner_cost(a)) + _horner_cost([t[1] for t in rest]) + 1
+            if best is None or (cost, -len(with_v)) < (best[0], -best[1]):
+                best = (cost, len(with_v), v, k)
+        _, _, v, k = best
+        with_v = [(c, tuple(x - (k if i == v else 0) for i, x in enumerate(e))) for c, e in terms if e[v] > 0]
+        rest = [(c, e) for c, e in terms if e[v] == 0]
+        a = self.emit(with_v)
+        if not rest:
+            return self._mul(a, self._pow(v, k))
+        b = self.emit(rest)
+        return self._fma(a, self._pow(v, k), b)
+
+
+class _Powers:
+    """x^k, y^k, dx^k, dy^k of one evaluation: packed pairs {x^k, y^k} and {dx^k, dy^k} built on demand (K2, mirror) or
+    per-variable values (K1 two-ray packed / scalar)."""
+
+    def __init__(self, lines, mode, stats):
+        self.lines, self.mode, self.stats, self.have = lines, mode, stats, {}
+
+    def get(self, base, k):  # base: 0 = X pair (or variable index in plain mode), 2 = D pair
+        if k == 1:
+            return self.base_name(base)
+        if (base, k) in self.have:
+            return self.have[(base, k)]
+        lo, hi = k // 2, k - k // 2
+        a, b = self.get(base, lo), self.get(base, hi)
+        name = "p%d_%d" % (base, k)
+        if self.mode == "scalar":
+            self.lines.append("    const float %s = %s * %s;" % (name, a, b))
+            self.stats["fmul"] += 1
+        else:
+            self.lines.append("    const float2 %s = __fmul2_rn(%s, %s);" % (name, a, b))
+            self.stats["fmul2"] += 1
+        self.have[(base, k)] = name
+        return name
+
+    def base_name(self, base):
+        if self.mode == "mirror":
+            return "X" if base == 0 else "D"
+        return "b%d" % base
+
+
+def emit_group_horner(name, signature, polys5, outputs, coefs: Coefs, packed=True, cname="C", imm_lambda=None):
+    """K1 (two-ray packed) or scalar bodies in Horner form over the folded polynomials."""
+    ty = "float2" if packed else "float"
+    lines = ["  LB_DEV void %s(%s) const {" % (name, signature), "    const %s b0 = b[0], b1 = b[1], b2 = b[2], b3 = b[3];" % ty]
+    stats = dict(fmul=0, fmul2=0, ffma=0, ffma2=0)
+    powers = _Powers(lines, "packed" if packed else "scalar", stats)
+
+    def cst(parts):
+        if imm_lambda is not None:
+            v = _f(sum(c * imm_lambda**e for c, e in parts))
+            return "make_float2(%s, %s)" % (v, v) if packed else v
+        j = coefs.scalar(parts)
+        return ("make_float2(%s.s[%d], %s.s[%d])" % (cname, j, cname, j)) if packed else "%s.s[%d]" % (cname, j)
+
+    for j, (poly, out) in enumerate(zip(polys5, outputs)):
+        f = fold(poly)
+        em = HornerEmitter(lines, packed, lambda v: "b%d" % v, lambda v, k: powers.get(v, k), cst, "h%d_" % j, stats)
+        terms = [(parts, e) for e, parts in f.items()]
+        lines.append("    %s = %s;" % (out, em.emit(terms) if terms else cst([(0.0, 0)])))
+    lines.append("  }")
+    return lines, stats["fmul"] + stats["fmul2"], stats["ffma"] + stats["ffma2"]
+
+
+def emit_mirror_group_horner(name, signature, pairs, coefs: Coefs, cname="C", imm_lambda=None):
+    """K2: lt_all in Horner form, pairs with mirrored supports on packed instructions, the others as two scalar schemes."""
+    lines = ["  LB_DEV void %s(%s) const {" % (name, signature),
+             "    const float2 X = make_float2(b[0], b[1]), D = make_float2(b[2], b[3]);"]
+    stats = dict(fmul=0, fmul2=0, ffma=0, ffma2=0)
+    powers = _Powers(lines, "mirror", stats)
+
+    def val(parts):
+        return sum(c * imm_lambda**e for c, e in parts)
+
+    def swap(x):
+        return "make_float2(%s.y, %s.x)" % (x, x)
+
+    def pvar(v):  # packed variable seen from P: x -> {x, y}, y -> {y, x}, dx -> {dx, dy}, dy -> {dy, dx}
+        base = "X" if v < 2 else "D"
+        return base if v % 2 == 0 else swap(base)
+
+    def ppow(v, k):
+        pk = powers.get(0 if v < 2 else 2, k)
+        return pk if v % 2 == 0 else swap(pk)
+
+    def svar(v):  # scalar variable
+        return ("X" if v < 2 else "D") + (".x" if v % 2 == 0 else ".y")
+
+    def spow(v, k):
+        return powers.get(0 if v < 2 else 2, k) + (".x" if v % 2 == 0 else ".y")
+
+    def pair_coef(cpq):
+        cp, cq = cpq
+        if imm_lambda is not None:
+            return "make_float2(%s, %s)" % (_f(val(cp)), _f(val(cq)))
+        if cp == cq:
+            j = coefs.scalar(cp)
+            return "make_float2(%s.s[%d], %s.s[%d])" % (cname, j, cname, j)
+        return "%s.p[%d]" % (cname, coefs.pair(cp, cq))
+
+    def scalar_coef(parts):
+        if imm_lambda is not None:
+            return _f(val(parts))
+        return "%s.s[%d]" % (cname, coefs.scalar(parts))
+
+    for k, (p5, q5, outP, outQ) in enumerate(pairs):
+        fp, fq = fold(p5), fold(q5)
+        if set(fp) == {mir(u) for u in fq} and fp:  # supports mirror each other: one packed scheme serves both
+            em = HornerEmitter(lines, True, pvar, ppow, pair_coef, "g%d_" % k, stats)
+            r = em.emit([((parts, fq[mir(e)]), e) for e, parts in fp.items()])
+            lines.append("    %s = %s.x;" % (outP, r) if not r.startswith("make_float2") and not r.startswith(cname) else
+                         "    { const float2 r_ = %s; %s = r_.x; %s = r_.y; }" % (r, outP, outQ))
+            if not r.startswith("make_float2") and not r.startswith(cname):
+                lines.append("    %s = %s.y;" % (outQ, r))
+        else:
+            for f, out, tag in ((fp, outP, "p"), (fq, outQ, "q")):
+                em = HornerEmitter(lines, False, svar, spow, scalar_coef, "g%d%s_" % (k, tag), stats)
+                terms = [(parts, e) for e, parts in f.items()]
+                lines.append("    %s = %s;" % (out, em.emit(terms) if terms else "0.0f"))
+    lines.append("  }")
+    return lines, stats

@@ -43,7 +43,9 @@ def test_camera_node_create_ray(ref, kw, monkeypatch):
     p = po_params(**kw)
     r, a = ref.RefCamera(p, img), ref.AdaptorCamera(p, img)
     sr, sa = r.state, a.state
-    assert sa.aperture_radius == sr.aperture_radius and sa.sensor_shift == sr.sensor_shift and sa.tan_fov == sr.tan_fov
+    assert sa.aperture_radius == sr.aperture_radius and sa.tan_fov == sr.tan_fov
+    if p.camera_type == abi.LB_CAMERA_POLYNOMIAL_OPTICS:  # the thin-lens setup does not touch Camera::sensor_shift (lentil.h:1663-1668)
+        assert sa.sensor_shift == sr.sensor_shift
     n = 20000
     w = int(round((n * 16 / 9) ** 0.5))
     ins = workloads.camera_samples(w, -(-n // w), 1, "cpu", 0, n, "linear")
