@@ -19,7 +19,7 @@ keeps: `roofline.splat_*` (device-resident value, executed FMA-slot fraction, re
 
 N > 1: one process per GPU.  Camera rays shard with no collective (every rank traces its own frame's
 worth of samples, weak scaling).  The splat frame is ONE frame for all ranks (strong scaling): source
-samples are dealt to the ranks in round-robin 4x4 pixel tiles, every rank accumulates a full-frame
+samples are dealt to the ranks in hashed pixel tiles, every rank accumulates a full-frame
 partial, lb_filter_reduce_scatter (one ncclReduceScatter per plane over NVLink) leaves every rank owning a
 pixel slab, which it resolves itself; lb_imager_resolve_gather collects the slabs on rank 0.
 """
@@ -48,7 +48,7 @@ CHUNK_RAYS = FRAME_W * FRAME_H * 4  # 33 177 600 rays per call on the e2e path (
 IN_KEYS = ("sx", "sy", "dsx", "dsy", "lensx", "lensy")
 CPU_SAMPLE_PER_THREAD = 200_000  # rays per host thread in the CPU legs (~1-2 s with the compiled reference)
 CPU_SPLAT_SOURCES_PER_THREAD = 100  # redistributed source samples per host thread in the CPU splat leg (2000 splats each, ~10 s in all)
-SPLAT_TILE = 4  # round-robin tile edge (pixels) of the multi-GPU source-sample partition: a highlight of ~10 px is shared by several ranks
+SPLAT_TILE = 1  # tile edge (pixels) of the hashed multi-GPU source-sample partition: pixel granularity balances ~10 px highlights to 1.05x the mean
 
 
 def camera_params():
@@ -584,11 +584,11 @@ def bench_splat(args, rank, world, local_rank, dev, barrier, max_over_ranks, sum
     img = workloads.disc_bokeh_image(250)
     cam = Camera(splat_params(), bokeh=img, device=local_rank)
     total = SPLAT_W * SPLAT_H * spp
-    # source samples: round-robin 64x64 pixel tiles over the ranks, the 16 samples of a pixel together
+    # source samples: hashed pixel tiles over the ranks, the 16 samples of a pixel together
     if world > 1:
         mine = workloads.tile_partition(SPLAT_W, SPLAT_H, spp, rank, world, tile=SPLAT_TILE, device=dev)
         fr = workloads.highlight_frame(SPLAT_W, SPLAT_H, spp, cam.state.tan_fov, dev, grid=SPLAT_GRID, samples=mine)
-        partition = f"round-robin {SPLAT_TILE}x{SPLAT_TILE} pixel tiles of source samples over {world} ranks; ncclReduceScatter per plane, per-rank resolve, gather on rank 0"
+        partition = f"hashed {SPLAT_TILE}x{SPLAT_TILE} pixel tiles of source samples over {world} ranks; ncclReduceScatter per plane, per-rank resolve, gather on rank 0"
     else:
         fr = workloads.highlight_frame(SPLAT_W, SPLAT_H, spp, cam.state.tan_fov, dev, grid=SPLAT_GRID)
         partition = "single GPU: whole frame, no collective"

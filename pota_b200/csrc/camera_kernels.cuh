@@ -63,8 +63,8 @@ LB_DEV FwRay trace_ray_fw_po(const E &ev, const CamConsts<float> &cam, float sx,
   // origin/direction *= -{1,.1,.01,.001} (lentil.h:395-416), then AiV3Normalize
 #pragma unroll
   for (int k = 0; k < 3; ++k) { r.o[k] = pos[k] * cam.unit_scale; dir[k] *= cam.unit_scale; }
-  const float len = sqrtf(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
-  const float inv = len != 0.f ? 1.0f / len : 0.f;
+  const float len2 = dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2];
+  const float inv = len2 > 0.f ? rsqrtf(len2) : (len2 == 0.f ? 0.f : len2);  // AiV3Normalize: 1 / length, 0 for the null vector (NaN stays NaN)
 #pragma unroll
   for (int k = 0; k < 3; ++k) r.d[k] = dir[k] * inv;
   // NaN bailout (lentil.h:421-425)
@@ -226,8 +226,8 @@ LB_DEV void finish_fw_ray(const CamConsts<float> &cam, const float out[4], bool 
   // origin/direction *= -{1,.1,.01,.001} (lentil.h:395-416), then AiV3Normalize
 #pragma unroll
   for (int k = 0; k < 3; ++k) { o[k] = pos[k] * cam.unit_scale; dir[k] *= cam.unit_scale; }
-  const float len = sqrtf(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
-  const float inv = len != 0.f ? 1.0f / len : 0.f;
+  const float len2 = dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2];
+  const float inv = len2 > 0.f ? rsqrtf(len2) : (len2 == 0.f ? 0.f : len2);  // AiV3Normalize: 1 / length, 0 for the null vector (NaN stays NaN)
   ok = success;
 #pragma unroll
   for (int k = 0; k < 3; ++k) {

@@ -60,7 +60,7 @@ struct FilterState {
     uint16_t *debug_samples = nullptr;
     float2 *crypto_cache = nullptr;   // [n_crypto][work_cap][crypto_cache_stride]
     int crypto_cache_stride = 0;
-    unsigned int *heads = nullptr;    // [2]
+    unsigned int *heads = nullptr;    // [4], see AovSet::work_heads
     cudaEvent_t done = nullptr;       // recorded after the last kernel that used this scratch
   };
   static constexpr int kScratch = 4;
@@ -207,7 +207,7 @@ void fill_aovs(const FilterState *f, AovSet &A, const lb_samples *S, const Filte
 
 int ensure_batch_capacity(FilterState *f, FilterState::Scratch *sc, size_t n, int crypto_depth) {
   const int stride = f->n_crypto ? std::max(crypto_depth, 1) : 0;
-  if (!sc->heads) CUF(cudaMalloc(&sc->heads, 2 * sizeof(unsigned)));
+  if (!sc->heads) CUF(cudaMalloc(&sc->heads, 4 * sizeof(unsigned)));
   if (!sc->done) {
     CUF(cudaEventCreateWithFlags(&sc->done, cudaEventDisableTiming));
     CUF(cudaEventRecord(sc->done, f->stream));
@@ -257,7 +257,7 @@ int accumulate_device(lb_camera *c, FilterState *f, const lb_samples *S, cudaStr
   CUF(cudaStreamWaitEvent(stream, sc->done, 0));    // the previous batch that used this scratch slot
   f->scattered = false;
   for (int a = 0; a < f->n_aov; ++a) f->res_valid[a] = false;
-  CUF(cudaMemsetAsync(sc->heads, 0, 2 * sizeof(unsigned), stream));
+  CUF(cudaMemsetAsync(sc->heads, 0, 4 * sizeof(unsigned), stream));
   CUF(launch_filter_classify(fc, A, io, sc->work, f->d_counters, f->sample_base, stream));
   if (cam_params(c).camera_type == LB_CAMERA_THINLENS)
     CUF(launch_filter_splat_thinlens(cam_consts(c), cam_thin(c), fc, A, io, sc->work, f->d_counters, f->sample_base, cam_num_sms(c), stream));

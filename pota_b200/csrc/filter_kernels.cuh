@@ -73,9 +73,12 @@ LB_DEV float channel_lambda(const FilterConsts &fc, int ch) {  // lentil_filter.
   return 0.55f;
 }
 
+// Attempts [t_begin, ...) of one work item.  t_end >= 0: the range [t_begin, t_end) lies inside the first n_samples attempts, all
+// certain to run (count_before(t) <= t < samples): a CHUNK, no stop rule needed.  t_end < 0: the tail of the sequential loop
+// from attempt t_begin = n_samples on, with `known_fails` failures among the attempts before it.  Returns the failures found.
 template <typename E>
-LB_DEV void splat_work_item(const E &ev, const CamConsts<float> &cam, const FilterConsts &fc, const AovSet &aovs, const SampleIO &s,
-                            const WorkItem &w, FilterCounters *counters, uint64_t sample_base) {
+LB_DEV int splat_work_item(const E &ev, const CamConsts<float> &cam, const FilterConsts &fc, const AovSet &aovs, const SampleIO &s,
+                           const WorkItem &w, FilterCounters *counters, uint64_t sample_base, int t_begin, int t_end, int known_fails) {
   const int lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
   const size_t i = w.sample;
@@ -92,8 +95,8 @@ LB_DEV void splat_work_item(const E &ev, const CamConsts<float> &cam, const Filt
   const int nchan = chroma ? 3 : 1;
 
   // warp-uniform bookkeeping of the stop rule
-  int next = 0;         // next attempt index (`total_samples_taken`) to hand out
-  int known_fails = 0;  // channel failures among COMPLETED attempts
+  int next = t_begin;   // next attempt index (`total_samples_taken`) to hand out
+  const int fails_before = known_fails;  // known_fails: channel failures among COMPLETED attempts
   unsigned n_splats = 0, n_attempts = 0, n_its = 0;
   // per-lane attempt state
   enum { IDLE = 0, RUNNING = 1, PENDING = 2 };  // PENDING: Newton loop ended, try not yet finished
@@ -108,7 +111,7 @@ LB_DEV void splat_work_item(const E &ev, const CamConsts<float> &cam, const Filt
     // It is divergent, scalar-ish code (transmittance polynomial, FP64 pixel mapping, RNG + CDF search), so it
     // runs only when kServiceBatch lanes are waiting for it (or nothing else is left to do): its cost is
     // shared by a batch of lanes instead of being paid by the whole warp for every single attempt.
-    const int limit = min(samples + known_fails, max_total);
+    const int limit = t_end >= 0 ? t_end : min(samples + known_fails, max_total);
     const unsigned running = __ballot_sync(0xffffffffu, state == RUNNING);
     const unsigned pending = __ballot_sync(0xffffffffu, state == PENDING);
     const unsigned idle = ~(running | pending);
@@ -157,7 +160,7 @@ LB_DEV void splat_work_item(const E &ev, const CamConsts<float> &cam, const Filt
       // hand the next CERTAIN attempts to idle lanes (the failures just learnt may have raised the limit)
       {
         const unsigned free_lanes = __ballot_sync(0xffffffffu, state == IDLE);
-        const int navail = max(min(samples + known_fails, max_total) - next, 0);
+        const int navail = max((t_end >= 0 ? t_end : min(samples + known_fails, max_total)) - next, 0);
         const int rank = __popc(free_lanes & lt_mask);
         if (state == IDLE && rank < navail) {
           state = RUNNING;
@@ -198,25 +201,70 @@ LB_DEV void splat_work_item(const E &ev, const CamConsts<float> &cam, const Filt
     atomicAdd(&counters->attempts, (unsigned long long)n_attempts);
     atomicAdd(&counters->newton_its, (unsigned long long)n_its);
   }
+  return known_fails - fails_before;
 }
 
 // (A variant with two attempt slots per lane and FFMA2/FMUL2 Newton bodies was built and measured in r01: correct, 20-30 % fewer
 // instructions, but 168 registers -> 12 warps/SM and 12 % slower; profiles/r01_k2_packed_experiment.txt.  Its successor is the
 // mirror-packed body of lensgen/emit_folded.py: packed over the lens symmetry instead of over two attempts, same register count.)
 
-// persistent kernel body: warps pull work items until the list is drained
+// Persistent kernel body.  A work item's first n_samples attempts are certain, so they can be dealt out in CHUNKS to whichever
+// warps are free; the warp that completes an item's last chunk knows the item's failure count and runs the tail of the
+// sequential loop (the `--count` re-draws, a handful of attempts on a few items).  Chunk size: the whole item while the list
+// holds several items per warp -- a warp that stays on one item keeps all its lanes refilled and drains them once per item --
+// and smaller when it does not (a rank of an 8-GPU run holds 1/8 of the frame's highlights: 1.5 items of ~5 ms per resident
+// warp, i.e. whole items would run in two rounds of which the second is half empty).
 template <typename E>
 LB_DEV void splat_persistent(const E &ev, const CamConsts<float> &cam, const FilterConsts &fc, const AovSet &aovs, const SampleIO &s,
-                             const WorkItem *__restrict__ work, FilterCounters *counters, uint64_t sample_base) {
+                             const WorkItem *__restrict__ work_, FilterCounters *counters, uint64_t sample_base) {
+  WorkItem *work = const_cast<WorkItem *>(work_);  // chunk_next / chunks_done / fails are updated in place
   const int lane = threadIdx.x & 31;
   const unsigned n_work = *((volatile unsigned *)&aovs.work_heads[0]);
+  const unsigned total_attempts = *((volatile unsigned *)&aovs.work_heads[2]);
+  const unsigned warps = gridDim.x * (blockDim.x >> 5);
+  unsigned chunk = 0x7fffffffu;  // whole items
+  if (n_work < 4u * warps) chunk = max(64u, ((total_attempts / (4u * warps)) + 31u) & ~31u);
   for (;;) {
-    unsigned idx = 0;
-    if (lane == 0) idx = atomicAdd(&aovs.work_heads[1], 1u);
+    unsigned idx = 0, c = 0;
+    if (lane == 0) {
+      for (;;) {
+        idx = *((volatile unsigned *)&aovs.work_heads[1]);
+        if (idx >= n_work) break;
+        c = atomicAdd(&work[idx].chunk_next, 1u);
+        if ((unsigned long long)c * chunk < (unsigned long long)work[idx].n_samples) break;
+        atomicMax(&aovs.work_heads[1], idx + 1u);  // this item's chunks are all handed out
+      }
+    }
     idx = __shfl_sync(0xffffffffu, idx, 0);
+    c = __shfl_sync(0xffffffffu, c, 0);
     if (idx >= n_work) break;
     const WorkItem w = work[idx];
-    splat_work_item(ev, cam, fc, aovs, s, w, counters, sample_base);
+    const unsigned n_chunks = (unsigned)(((unsigned long long)w.n_samples + chunk - 1) / chunk);
+    int t0 = (int)min((unsigned long long)c * chunk, (unsigned long long)w.n_samples);
+    int t1 = (int)min((unsigned long long)t0 + chunk, (unsigned long long)w.n_samples);
+    int known = 0;
+    // ONE call site (the body is ~30 KB of straight-line code): first the chunk, then -- only for the warp that completes the
+    // item's last chunk, and only if the item had failures -- the tail of the sequential loop
+    for (bool tail = false;; tail = true) {
+      const int fails = splat_work_item(ev, cam, fc, aovs, s, w, counters, sample_base, t0, t1, known);
+      if (tail) break;
+      unsigned done = 0, all_fails = 0;
+      if (lane == 0) {
+        if (fails) atomicAdd(&work[idx].fails, (unsigned)fails);
+        __threadfence();
+        done = atomicAdd(&work[idx].chunks_done, 1u) + 1u;
+        if (done == n_chunks) {
+          __threadfence();
+          all_fails = *((volatile unsigned *)&work[idx].fails);
+        }
+      }
+      done = __shfl_sync(0xffffffffu, done, 0);
+      all_fails = __shfl_sync(0xffffffffu, all_fails, 0);
+      if (done != n_chunks || all_fails == 0u) break;
+      t0 = (int)w.n_samples;  // the attempts the failures bought (lentil_filter.cpp:272-287): sequential rule from here on
+      t1 = -1;
+      known = (int)all_fails;
+    }
   }
 }
 

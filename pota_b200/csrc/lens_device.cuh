@@ -216,8 +216,36 @@ LB_DEV void cs_to_cylinder(const T pos[3], const T dir_in[3], T center, T R, boo
   odx = d0 * ex0 + d2 * ex2;
   ody = d0 * ey0 + d1 * ey1 + d2 * ey2;
 }
+LB_DEV float sqrt_approx(float x);
+// sphereToCs (lens.h:99-125) for the float kernels with the per-camera reciprocals of the outer pupil sphere: MUFU.SQRT / MUFU.RSQ /
+// MUFU.RCP (1-2 ulp) instead of four IEEE divisions and three IEEE square roots with their fix-up sequences and slow-path branches
+template <typename C>
+LB_DEV void sphere_to_cs_fast(const C &cam, const float out[4], float pos[3], float dir[3]) {
+  const float px = out[0], py = out[1], dx = out[2], dy = out[3];
+  const float r2 = px * px + py * py;
+  const float nx = px * cam.inv_outer_R, ny = py * cam.inv_outer_R;
+  const float nz = sqrt_approx(fmaxf(0.0f, cam.outer_R2 - r2)) * cam.abs_inv_outer_R;
+  const float tz = sqrt_approx(fmaxf(0.0f, 1.0f - dx * dx - dy * dy));
+  const float il = rsqrtf(nz * nz + nx * nx);
+  const float ex0 = nz * il, ex2 = -nx * il;
+  const float ey0 = ny * ex2, ey1 = nz * ex0 - nx * ex2, ey2 = -ny * ex0;
+  dir[0] = dx * ex0 + dy * ey0 + tz * nx;
+  dir[1] = dy * ey1 + tz * ny;
+  dir[2] = dx * ex2 + dy * ey2 + tz * nz;
+  pos[0] = px;
+  pos[1] = py;
+  pos[2] = -fminf(r2, cam.outer_R2) * t_rcp(fmaf(cam.outer_R, nz, cam.outer_R));  // R*nz - R without cancellation
+}
 template <typename T, typename C>
 LB_DEV void outer_to_cs(const C &cam, const T out[4], T pos[3], T dir[3]) {  // lentil.h:387-389
+#ifndef LB_GENERIC_LT_TAIL
+  if constexpr (sizeof(T) == 4) {
+    if (cam.outer_geom == 0) {
+      sphere_to_cs_fast(cam, out, pos, dir);
+      return;
+    }
+  }
+#endif
   if (cam.outer_geom == 0) sphere_to_cs(out[0], out[1], out[2], out[3], cam.outer_R, pos, dir);
   else cylinder_to_cs(out[0], out[1], out[2], out[3], -cam.outer_R, cam.outer_R, cam.outer_geom == 1, pos, dir);
 }
@@ -376,7 +404,7 @@ LB_DEV void lt_iterate_tail(const C &cam, const T scene[3], T ax, T ay, const T 
 }
 // sqrt for non-negative finite arguments on the special-function unit (MUFU.SQRT, 1-2 ulp); sqrtf is a MUFU.RSQ plus a
 // fix-up sequence with a slow-path branch
-LB_DEV float sqrt_approx(float x) {
+LB_DEV float sqrt_approx(float x) {  // (declared above for sphere_to_cs_fast)
   float r;
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;

@@ -26,7 +26,7 @@ def main():
     ap.add_argument("--spp", type=int, default=16)
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--combine", default="scatter", choices=["scatter", "reduce"])
-    ap.add_argument("--tile", type=int, default=16)
+    ap.add_argument("--tile", type=int, default=4)
     a = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -98,7 +98,7 @@ def main():
         total_ms = float(tmax[0] + tmax[1] + tmax[2])
         block_gb = W * H * (4 * len(aovs) + 1) * 4 / 1e9
         print("C5 " + json.dumps({"config": f"C5 {W}x{H}x{a.spp}spp, {len(aovs)} AOVs (9 gaussian RGBA + 1 closest), {world} GPU(s)", "combine": a.combine,
-                          "partition": f"round-robin {a.tile}x{a.tile} pixel tiles", "accumulate_ms": float(tmax[0]),
+                          "partition": f"hashed {a.tile}x{a.tile} pixel tiles", "accumulate_ms": float(tmax[0]),
                           "reduce_ms": float(tmax[1]), "resolve_gather_ms": float(tmax[2]), "splats": splats, "splats_per_s": splats / (total_ms * 1e-3),
                           "framebuffer_block_GB": block_gb, "reduce_GBps_per_rank": block_gb / (float(tmax[1]) * 1e-3) if world > 1 else None}))
     if world > 1:
