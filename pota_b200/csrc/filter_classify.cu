@@ -175,10 +175,12 @@ k_filter_classify(const __grid_constant__ FilterConsts fc, const __grid_constant
   // append redistributed samples to the work list, one atomic per warp
   const unsigned mask = __ballot_sync(0xffffffffu, redistribute);
   const unsigned warp_samples = __reduce_add_sync(0xffffffffu, redistribute ? (unsigned)samples : 0u);
+  const unsigned warp_max = __reduce_max_sync(0xffffffffu, redistribute ? (unsigned)samples : 0u);
   unsigned base = 0;
   if (lane == 0 && mask) {
     base = atomicAdd(&aovs.work_heads[0], (unsigned)__popc(mask));
     atomicAdd(&aovs.work_heads[2], warp_samples);  // attempts the splat kernel is certain to run: sizes its work units
+    atomicMax(&aovs.work_heads[3], warp_max);
     atomicAdd(&counters->redistributed, (unsigned long long)__popc(mask));
   }
   base = __shfl_sync(0xffffffffu, base, 0);
@@ -188,7 +190,7 @@ k_filter_classify(const __grid_constant__ FilterConsts fc, const __grid_constant
     w.n_samples = (uint32_t)samples;
     w.add_energy = add_energy;
     w.csp[0] = csp[0]; w.csp[1] = csp[1]; w.csp[2] = csp[2];
-    w.chunk_next = w.chunks_done = w.fails = w.pad_ = 0u;
+    w.chunks_done = w.fails = 0u;
     work[base + __popc(mask & ((1u << lane) - 1u))] = w;
   }
   // (samples consumed and pass-through adds are counted on the host: three same-address reductions per warp here cost

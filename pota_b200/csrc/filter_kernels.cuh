@@ -217,28 +217,26 @@ LB_DEV int splat_work_item(const E &ev, const CamConsts<float> &cam, const Filte
 template <typename E>
 LB_DEV void splat_persistent(const E &ev, const CamConsts<float> &cam, const FilterConsts &fc, const AovSet &aovs, const SampleIO &s,
                              const WorkItem *__restrict__ work_, FilterCounters *counters, uint64_t sample_base) {
-  WorkItem *work = const_cast<WorkItem *>(work_);  // chunk_next / chunks_done / fails are updated in place
+  WorkItem *work = const_cast<WorkItem *>(work_);  // chunks_done / fails are updated in place
   const int lane = threadIdx.x & 31;
   const unsigned n_work = *((volatile unsigned *)&aovs.work_heads[0]);
   const unsigned total_attempts = *((volatile unsigned *)&aovs.work_heads[2]);
   const unsigned warps = gridDim.x * (blockDim.x >> 5);
+  const unsigned max_samples = *((volatile unsigned *)&aovs.work_heads[3]);
   unsigned chunk = 0x7fffffffu;  // whole items
   if (n_work < 4u * warps) chunk = max(64u, ((total_attempts / (4u * warps)) + 31u) & ~31u);
+  // work-unit tickets: ticket -> (item, chunk) with a fixed number of chunk slots per item (1 for whole items); an item
+  // shorter than its slots leaves empty tickets, which cost one atomic each
+  const unsigned slots = chunk >= max_samples ? 1u : (max_samples + chunk - 1u) / chunk;
+  const unsigned long long n_tickets = (unsigned long long)n_work * slots;
   for (;;) {
-    unsigned idx = 0, c = 0;
-    if (lane == 0) {
-      for (;;) {
-        idx = *((volatile unsigned *)&aovs.work_heads[1]);
-        if (idx >= n_work) break;
-        c = atomicAdd(&work[idx].chunk_next, 1u);
-        if ((unsigned long long)c * chunk < (unsigned long long)work[idx].n_samples) break;
-        atomicMax(&aovs.work_heads[1], idx + 1u);  // this item's chunks are all handed out
-      }
-    }
-    idx = __shfl_sync(0xffffffffu, idx, 0);
-    c = __shfl_sync(0xffffffffu, c, 0);
-    if (idx >= n_work) break;
+    unsigned ticket = 0;
+    if (lane == 0) ticket = atomicAdd(&aovs.work_heads[1], 1u);
+    ticket = __shfl_sync(0xffffffffu, ticket, 0);
+    if (ticket >= n_tickets) break;
+    const unsigned idx = ticket / slots, c = ticket - idx * slots;
     const WorkItem w = work[idx];
+    if ((unsigned long long)c * chunk >= (unsigned long long)w.n_samples) continue;  // an empty slot of a short item
     const unsigned n_chunks = (unsigned)(((unsigned long long)w.n_samples + chunk - 1) / chunk);
     int t0 = (int)min((unsigned long long)c * chunk, (unsigned long long)w.n_samples);
     int t1 = (int)min((unsigned long long)t0 + chunk, (unsigned long long)w.n_samples);

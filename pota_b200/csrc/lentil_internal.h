@@ -90,8 +90,8 @@ struct AovSet {
   float2 *crypto_cache[kMaxAov];     // this batch: [n][max(crypto_depth,1)] merged {id, weight} of each sample, packed,
                                      // kCryptoFree-terminated (cryptomatte_construct_cache, lentil.h:779-811)
   int32_t crypto_slots, crypto_depth;
-  unsigned int *work_heads;          // this batch's work list: [0] items appended by classify, [1] next item handed to a warp,
-                                     // [2] sum of n_samples over the items (classify), [3] unused
+  unsigned int *work_heads;          // this batch's work list: [0] items appended by classify, [1] next work-unit ticket,
+                                     // [2] sum and [3] maximum of n_samples over the items (classify)
 };
 constexpr uint32_t kCryptoFree = 0xFFFFFFFFu;  // a NaN bit pattern: Cryptomatte hashes are never NaN
 constexpr int kCryptoMaxDepth = 8;
@@ -113,10 +113,8 @@ struct WorkItem {  // one redistributed source sample
   float add_energy;    // fitted_bidir_add_energy
   float csp[3];        // camera-space position after unit scaling / skydome substitution (lentil_filter.cpp:121-148)
   // PO splat kernel: the first n_samples attempts are dealt out in chunks to whichever warps are free (filter_kernels.cuh)
-  uint32_t chunk_next;   // next chunk to hand out
   uint32_t chunks_done;  // chunks completed
   uint32_t fails;        // failed attempts among the completed chunks
-  uint32_t pad_;
 };
 
 struct FilterCounters {  // device-side mirror of lb_filter_stats
