@@ -62,6 +62,8 @@ struct FilterState {
     int crypto_cache_stride = 0;
     unsigned int *heads = nullptr;    // [4], see AovSet::work_heads
     cudaEvent_t done = nullptr;       // recorded after the last kernel that used this scratch
+    cudaStream_t last_stream = nullptr;
+    bool used = false;
   };
   static constexpr int kScratch = 4;
   Scratch scratch[kScratch];
@@ -239,8 +241,21 @@ int accumulate_device(lb_camera *c, FilterState *f, const lb_samples *S, cudaStr
   if (S->n > 0xFFFFFFFFull) return lb_fail(LB_ERR_INVALID, "batch larger than 2^32 samples");
   if (S->crypto_depth < 0 || S->crypto_depth > LB_CRYPTO_MAX_DEPTH) return lb_fail(LB_ERR_INVALID, "crypto_depth outside [0, LB_CRYPTO_MAX_DEPTH]");
   // closest-filter AOVs fetch the winning sample's value per batch (launch_closest_gather): batches in order, one slot
-  FilterState::Scratch *sc = &f->scratch[(f->has_closest || f->has_debug_closest) ? 0 : f->next_scratch];
-  f->next_scratch = (f->next_scratch + 1) % FilterState::kScratch;
+  FilterState::Scratch *sc = &f->scratch[0];
+  if (!(f->has_closest || f->has_debug_closest)) {
+    // the first slot whose previous batch has finished (serial callers keep reusing slot 0 and its allocations); when all
+    // are in flight, the next one in turn -- the new batch then queues behind that slot's batch on the device
+    // a slot last used on this very stream needs no waiting at all (stream order), so a caller that issues frame after
+    // frame on one stream stays on one slot
+    int pick = -1;
+    for (int i = 0; i < FilterState::kScratch && pick < 0; ++i)
+      if (f->scratch[i].used && f->scratch[i].last_stream == stream) pick = i;
+    for (int i = 0; i < FilterState::kScratch && pick < 0; ++i)
+      if (!f->scratch[i].done || cudaEventQuery(f->scratch[i].done) == cudaSuccess) pick = i;
+    cudaGetLastError();  // cudaErrorNotReady of the queries is not an error
+    if (pick < 0) { pick = f->next_scratch; f->next_scratch = (f->next_scratch + 1) % FilterState::kScratch; }
+    sc = &f->scratch[pick];
+  }
   int rc = ensure_batch_capacity(f, sc, S->n, S->crypto_depth);
   if (rc != LB_OK) return rc;
   FilterConsts fc;
@@ -266,6 +281,8 @@ int accumulate_device(lb_camera *c, FilterState *f, const lb_samples *S, cudaStr
                             cam_num_sms(c), stream));
   if (f->has_closest || f->has_debug_closest) CUF(launch_closest_gather(fc, A, io, f->sample_base, stream));
   CUF(cudaEventRecord(sc->done, stream));
+  sc->last_stream = stream;
+  sc->used = true;
   f->sample_base += S->n;
   f->samples_seen += S->n;
   return LB_OK;
