@@ -4,8 +4,6 @@
 
 namespace lb {
 
-constexpr int kSplatBlock = 128;
-
 __global__ void __launch_bounds__(kSplatBlock)
 k_filter_splat_table(const __grid_constant__ LensTable lens, const __grid_constant__ CamConsts<float> cam,
                      const __grid_constant__ FilterConsts fc, const __grid_constant__ AovSet aovs, const __grid_constant__ SampleIO s,

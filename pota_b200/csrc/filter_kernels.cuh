@@ -28,6 +28,7 @@ namespace lb {
 #define LB_SERVICE_BATCH 8
 #endif
 constexpr int kServiceBatch = LB_SERVICE_BATCH;
+constexpr int kSplatBlock = 128;  // threads per CTA of every splat kernel
 
 // aperture point of attempt `total`, try `tries` (lentil.h:594-609)
 LB_DEV void bw_aperture_sample(const CamConsts<float> &cam, uint32_t seed_base, uint32_t total, int tries, float &ax, float &ay) {
@@ -105,6 +106,8 @@ LB_DEV int splat_work_item(const E &ev, const CamConsts<float> &cam, const Filte
   float ax = 0.f, ay = 0.f, lambda = 0.55f;
   LtState<float> st;
   lt_init(st);
+  // (r02, measured and withdrawn: the aperture points of the next 32 attempts precomputed by the converged warp into a
+  // shared-memory ring instead of inside the divergent service phase -- 58.53 vs 58.58 ms on the C3 frame, no gain.)
 
   for (;;) {
     // ---- service phase: finish ended tries, hand out new attempts, splat -------------------------------
