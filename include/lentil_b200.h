@@ -132,7 +132,8 @@ LB_API int lb_lens_count(void);
 LB_API const char *lb_lens_name(int lens_model); /* LensModelNames, pota_cpp_lenses.h */
 LB_API const char *lb_last_error(void);
 /* "lentil_b200 <major>.<minor>.<patch> (sm_100a)".  0.2.0: lb_frame_desc, lb_samples and lb_filter_stats grew at their
- * ends (cryptomatte); 0.3.0: lb_samples grew at its end (world_to_camera).  Callers built against an older minor must be
+ * ends (cryptomatte); 0.3.0: lb_samples grew at its end (world_to_camera); 0.4.0: lb_filter_stats grew at its end
+ * (tile_splats).  Callers built against an older minor must be
  * recompiled. */
 LB_API const char *lb_version(void);
 
@@ -181,6 +182,12 @@ LB_API int lb_bench_fp32_peak(int device, double *tflops_out);
 /* On-box throughput of 16-byte vector reductions (red.global.add.v4.f32) at random pixels of a `megabytes` MB
  * plane, in GB/s: roofline denominator of the splat accumulate. */
 LB_API int lb_bench_red_peak(int device, int megabytes, double *gbytes_per_s_out);
+/* The splat accumulate alone (RGBA + filter weight = 20 B per splat at pseudo-random pixels), in 1e9 splats/s:
+ * mode 0 = red.global.add.v4.f32 + red.global.add.f32 into planes of `megabytes` MB (what the splat kernels do,
+ * Camera::add_to_buffer lentil.h:823-851); mode 1 = a 96x96-pixel shared-memory tile updated with float atomics and
+ * flushed once with vector reductions; mode 2 = the same tile with native 32-bit integer atomics (the floor of any
+ * shared-memory-atomic tile).  Evidence for where the accumulate should live on this part. */
+LB_API int lb_bench_splat_accum(int device, int mode, int megabytes, double *gsplats_per_s_out);
 
 /* Known-answer hook for the device-side integer / float primitives (global.h:32-57 tea<8> and rng, lens.h:17-37
  * fast_sin / fast_cos): for n seed pairs (v0, v1) computes on the device t = tea<8>(v0, v1), four rng() draws seeded
@@ -251,6 +258,7 @@ typedef struct lb_filter_stats {
   uint64_t attempts;      /* reverse-trace attempts (total_samples_taken summed) */
   uint64_t passthrough;   /* filter_and_add_to_buffer_new adds (:243-246) */
   uint64_t crypto_dropped;/* cryptomatte contributions lost because a pixel already held crypto_slots other ids */
+  uint64_t tile_splats;   /* of `splats`: accumulated in a shared-memory window first, reaching L2 merged (thin-lens tile kernel) */
 } lb_filter_stats;
 
 /* setup_filter (lentil.h:1056-1117): allocates zeroed device framebuffers. */

@@ -149,7 +149,7 @@ class Samples(C.Structure):
 
 
 class FilterStats(C.Structure):
-    _fields_ = [(n, C.c_uint64) for n in ("samples", "redistributed", "splats", "attempts", "passthrough", "crypto_dropped")]
+    _fields_ = [(n, C.c_uint64) for n in ("samples", "redistributed", "splats", "attempts", "passthrough", "crypto_dropped", "tile_splats")]
 
 
 def host_samples(n_aov, px, py, rgba, pos_cs, inv_density, aov_values=None, raydir=None, transmission=None, flags=None, crypto=None,

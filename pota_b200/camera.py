@@ -29,7 +29,7 @@ EXPORTS = [
     "lb_camera_create_rays", "lb_camera_create_rays_host", "lb_camera_reverse_rays", "lb_camera_lens_work",
     "lb_filter_begin", "lb_filter_accumulate", "lb_filter_accumulate_host", "lb_filter_get_stats",
     "lb_filter_newton_iterations", "lb_imager_resolve", "lb_imager_resolve_host", "lb_filter_buffers", "lb_filter_buffers_host", "lb_filter_crypto_host",
-    "lb_bench_fp32_peak", "lb_bench_red_peak", "lb_camera_set_pupil_geometry", "lb_camera_kernel_kind", "lb_comm_unique_id", "lb_comm_init", "lb_filter_set_sample_base", "lb_filter_reduce", "lb_comm_destroy",
+    "lb_bench_fp32_peak", "lb_bench_red_peak", "lb_bench_splat_accum", "lb_camera_set_pupil_geometry", "lb_camera_kernel_kind", "lb_comm_unique_id", "lb_comm_init", "lb_filter_set_sample_base", "lb_filter_reduce", "lb_comm_destroy",
     "lb_filter_reduce_scatter", "lb_filter_slab", "lb_imager_resolve_gather", "lb_debug_primitives",
 ]  # fmt: skip
 
@@ -74,6 +74,7 @@ def lib():
         L.lb_bench_fp32_peak.argtypes = [i, C.POINTER(C.c_double)]
         L.lb_camera_kernel_kind.argtypes = [vp]
         L.lb_bench_red_peak.argtypes = [i, i, C.POINTER(C.c_double)]
+        L.lb_bench_splat_accum.argtypes = [i, i, i, C.POINTER(C.c_double)]
         L.lb_camera_set_pupil_geometry.argtypes = [vp, i, i]
         L.lb_comm_unique_id.argtypes = [C.c_char_p]
         L.lb_comm_init.argtypes = [vp, i, i, C.c_char_p]

@@ -167,7 +167,7 @@ k_filter_classify(const __grid_constant__ FilterConsts fc, const __grid_constant
         }
         if (pass && head) {
           if (aovs.role[a] == 1 /*RGBA*/) atomicAdd(aovs.weight + pixel, w);
-          atomicAdd(aovs.buffer[a] + pixel, r);
+          if (aovs.add_zeros || r.x != 0.0f || r.y != 0.0f || r.z != 0.0f || r.w != 0.0f) atomicAdd(aovs.buffer[a] + pixel, r);  // see add_to_buffer
         }
       }
     }

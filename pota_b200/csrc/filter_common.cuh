@@ -34,7 +34,10 @@ LB_DEV void add_to_buffer(const AovSet &aovs, int a, unsigned pixel, float4 v, f
     r.y = (v.y + add_energy) * filter_weight * rgb_weight[1];
     r.z = (v.z + add_energy) * filter_weight * rgb_weight[2];
     r.w = (v.w + add_energy) * filter_weight;
-    atomicAdd(aovs.buffer[a] + pixel, r);
+    // An all-zero contribution is not sent: adding +-0 changes no bit of a buffer (it starts at +0 and round-to-nearest sums never
+    // produce -0), and most AOVs of a production set are zero for most samples (a per-light AOV holds one light's samples) --
+    // at 8K x 10 AOVs the planes are not L2-resident and every reduction is a DRAM read-modify-write.  NaNs compare unequal: sent.
+    if (aovs.add_zeros || r.x != 0.0f || r.y != 0.0f || r.z != 0.0f || r.w != 0.0f) atomicAdd(aovs.buffer[a] + pixel, r);
   } else {
     if (aovs.role[a] != 2) atomicMin(aovs.zkey + pixel, closest_key(depth, sample_global));
     else if (v.x != 0.0f) atomicMin(aovs.zkey_debug + pixel, closest_key(depth, sample_global));
@@ -77,15 +80,16 @@ LB_DEV void crypto_add(const AovSet &aovs, int a, size_t i, bool on, unsigned pi
 
 // every AOV of one splat (lentil_filter.cpp:295-298 / :442-445).  Warp-converged: the source sample i and with it
 // the AOV values are warp-uniform, the target pixel is per lane (< 0: this lane has nothing to add).
+// skip_aov: an AOV this lane has already accumulated elsewhere (the shared-memory window of the thin-lens tile kernel), or -1.
 LB_DEV void splat_all_aovs(const FilterConsts &fc, const AovSet &aovs, const SampleIO &s, size_t i, float debug_val, int pixel,
                            float add_energy, float depth, float weight, const float rgb_weight[3], uint64_t sample_global,
-                           FilterCounters *counters) {
+                           FilterCounters *counters, int skip_aov = -1) {
   for (int a = 0; a < fc.n_aov; ++a) {
     if (aovs.filter[a] == 2) {
       crypto_add(aovs, a, i, pixel >= 0, (unsigned)pixel, weight, counters);
     } else {
       const float4 v = aov_value(aovs, s, a, i, debug_val);
-      if (pixel >= 0) add_to_buffer(aovs, a, (unsigned)pixel, v, add_energy, depth, weight, rgb_weight, sample_global);
+      if (pixel >= 0 && a != skip_aov) add_to_buffer(aovs, a, (unsigned)pixel, v, add_energy, depth, weight, rgb_weight, sample_global);
     }
   }
 }

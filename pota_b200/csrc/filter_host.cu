@@ -60,7 +60,7 @@ struct FilterState {
     uint16_t *debug_samples = nullptr;
     float2 *crypto_cache = nullptr;   // [n_crypto][work_cap][crypto_cache_stride]
     int crypto_cache_stride = 0;
-    unsigned int *heads = nullptr;    // [4], see AovSet::work_heads
+    unsigned int *heads = nullptr;    // [kWorkHeads], see AovSet::work_heads
     cudaEvent_t done = nullptr;       // recorded after the last kernel that used this scratch
     cudaStream_t last_stream = nullptr;
     bool used = false;
@@ -186,6 +186,8 @@ void fill_aovs(const FilterState *f, AovSet &A, const lb_samples *S, const Filte
   const float *const *values = S ? S->aov_values : nullptr;
   A.crypto_slots = f->crypto_slots;
   A.crypto_depth = S ? S->crypto_depth : 0;
+  const bool add_zeros = getenv("LB_ADD_ZEROS") && getenv("LB_ADD_ZEROS")[0] == '1';
+  A.add_zeros = add_zeros ? 1 : 0;
   for (int a = 0; a < f->n_aov; ++a) {
     A.buffer[a] = (float4 *)(f->block + (size_t)a * f->npx_pad * 4);
     A.values[a] = values ? (const float4 *)values[a] : nullptr;
@@ -209,7 +211,7 @@ void fill_aovs(const FilterState *f, AovSet &A, const lb_samples *S, const Filte
 
 int ensure_batch_capacity(FilterState *f, FilterState::Scratch *sc, size_t n, int crypto_depth) {
   const int stride = f->n_crypto ? std::max(crypto_depth, 1) : 0;
-  if (!sc->heads) CUF(cudaMalloc(&sc->heads, 4 * sizeof(unsigned)));
+  if (!sc->heads) CUF(cudaMalloc(&sc->heads, kWorkHeads * sizeof(unsigned)));
   if (!sc->done) {
     CUF(cudaEventCreateWithFlags(&sc->done, cudaEventDisableTiming));
     CUF(cudaEventRecord(sc->done, f->stream));
@@ -272,7 +274,7 @@ int accumulate_device(lb_camera *c, FilterState *f, const lb_samples *S, cudaStr
   CUF(cudaStreamWaitEvent(stream, sc->done, 0));    // the previous batch that used this scratch slot
   f->scattered = false;
   for (int a = 0; a < f->n_aov; ++a) f->res_valid[a] = false;
-  CUF(cudaMemsetAsync(sc->heads, 0, 4 * sizeof(unsigned), stream));
+  CUF(cudaMemsetAsync(sc->heads, 0, kWorkHeads * sizeof(unsigned), stream));
   CUF(launch_filter_classify(fc, A, io, sc->work, f->d_counters, f->sample_base, stream));
   if (cam_params(c).camera_type == LB_CAMERA_THINLENS)
     CUF(launch_filter_splat_thinlens(cam_consts(c), cam_thin(c), fc, A, io, sc->work, f->d_counters, f->sample_base, cam_num_sms(c), stream));
@@ -523,6 +525,7 @@ int lb_filter_get_stats(lb_camera *c, lb_filter_stats *out) {
   out->samples = f->samples_seen; out->redistributed = h.redistributed; out->splats = h.splats;
   out->attempts = h.attempts; out->passthrough = f->samples_seen - h.redistributed;
   out->crypto_dropped = h.crypto_dropped;
+  out->tile_splats = h.tile_splats;
   return LB_OK;
 }
 

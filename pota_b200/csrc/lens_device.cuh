@@ -125,15 +125,34 @@ LB_DEV int upper_bound_f(const float *__restrict__ a, int n, float v) {
 // thin-lens splat kernel stalls on the searches' dependent loads, but it is the L1's wavefront rate that bounds it -- every lane
 // reads another row of the column table, 32 wavefronts per load instruction -- and 64 loads per attempt instead of 16 took the
 // kernel from 3.4 ms to 8.8 ms on the C3 frame.  profiles/r02_thinlens_splat_ncu.txt)
+// The same upper_bound through a guide table (host: BokehTables::build_guide): bucket k = floor(v * K) holds the window
+// {lo, hi} = {upper_bound(a, k/K), upper_bound(a, (k+1)/K)}, which contains upper_bound(a, v) because a is sorted; the
+// window holds about n/K entries (one, for the 250-pixel kernels), so the search is one guide load plus ~one table load
+// instead of log2(n) dependent loads on 32 different cache lines per warp.  Bucket 0 starts at 0 and the last bucket ends
+// at n, so v outside [0, 1) still gets the full search's answer; a NaN takes the full search.
+LB_DEV int upper_bound_guided(const float *__restrict__ a, const uint32_t *__restrict__ guide, int n, float v) {
+  if (!(v == v)) return upper_bound_f(a, n, v);
+  int k = (int)(v * (float)kBokehGuide);
+  k = k < 0 ? 0 : (k > kBokehGuide - 1 ? kBokehGuide - 1 : k);
+  const uint32_t g = __ldg(guide + k);
+  int lo = (int)(g & 0xFFFFu), len = (int)(g >> 16) - lo;
+  while (len > 0) {
+    const int half = len >> 1;
+    if (!(v < __ldg(a + lo + half))) { lo += half + 1; len -= half + 1; } else len = half;
+  }
+  return lo;
+}
 template <typename T, typename C>
 LB_DEV void bokeh_sample(const C &cam, float randomNumberRow, float randomNumberColumn, T &lx, T &ly) {
   const int n = cam.bokeh_n;
-  int r = upper_bound_f(cam.cdf_row, n, randomNumberRow);
+  const bool guided = cam.guide_row != nullptr;
+  int r = guided ? upper_bound_guided(cam.cdf_row, cam.guide_row, n, randomNumberRow) : upper_bound_f(cam.cdf_row, n, randomNumberRow);
   if (r >= n) r = n - 1;
   const int actualPixelRow = __ldg(cam.row_idx + r);
   const int recalulatedPixelRow = actualPixelRow - ((n - 1) / 2);
   const int startPixel = actualPixelRow * n;
-  int c = startPixel + upper_bound_f(cam.cdf_col + startPixel, n, randomNumberColumn);
+  int c = startPixel + (guided ? upper_bound_guided(cam.cdf_col + startPixel, cam.guide_col + (size_t)actualPixelRow * kBokehGuide, n, randomNumberColumn)
+                               : upper_bound_f(cam.cdf_col + startPixel, n, randomNumberColumn));
   if (c >= startPixel + n) c = startPixel + n - 1;
   const int actualPixelColumn = __ldg(cam.col_idx + c);
   const int relativePixelColumn = actualPixelColumn - startPixel;

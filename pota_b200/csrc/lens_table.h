@@ -31,6 +31,8 @@ struct LensTable {
   Term t[kMaxTerms];
 };
 
+constexpr int kBokehGuide = 256;  // buckets of [0, 1) per guided CDF search (a power of two: k/K is exact in float)
+
 // Per-camera scalars every ray needs (struct Camera, lentil.h:106-160 + setup results).
 template <typename T>
 struct CamConsts {
@@ -56,6 +58,8 @@ struct CamConsts {
   const int32_t *row_idx;
   const float *cdf_col;
   const int32_t *col_idx;
+  const uint32_t *guide_row;  // kBokehGuide {lo, hi} search windows of cdf_row, null = full binary search
+  const uint32_t *guide_col;  // bokeh_n x kBokehGuide windows of the rows of cdf_col
   T inv_outer_R, abs_inv_outer_R, outer_R2;  // 1/R, 1/|R|, R^2 of the outer pupil sphere (lt_iterate_tail_sphere)
   double lambda_exact;    // wavelength in double: the host folds it into the polynomial coefficients (gen/, EvalFA / EvalFB)
 };

@@ -121,6 +121,30 @@ struct BokehTables {
   int n = 0;
   std::vector<float> cdf_row, cdf_col;
   std::vector<int> row_idx, col_idx;
+  // Guide tables ("cutpoint method") for the two upper_bound searches of bokehSample: entry k packs
+  // {lo = upper_bound(cdf, k/K), hi = upper_bound(cdf, (k+1)/K)} as two 16-bit halves, so a search for v in
+  // [k/K, (k+1)/K) only has to look at cdf[lo..hi) -- the same index the full binary search returns, found with ~1
+  // dependent load instead of log2(n).  Empty when a table is not sorted or n does not fit 16 bits (full search then).
+  std::vector<uint32_t> guide_row, guide_col;
+  static void build_guide(const float *cdf, int n, uint32_t *g) {
+    int prev = 0;  // bucket 0 starts at 0 (v < 0), the last bucket ends at n (v >= 1)
+    for (int k = 0; k < kBokehGuide; ++k) {
+      const int hi = k + 1 == kBokehGuide ? n : (int)(std::upper_bound(cdf, cdf + n, (float)(k + 1) / (float)kBokehGuide) - cdf);
+      g[k] = (uint32_t)prev | ((uint32_t)hi << 16);
+      prev = hi;
+    }
+  }
+  void build_guides() {
+    guide_row.clear(); guide_col.clear();
+    if (n <= 0 || n > 65535) return;
+    if (!std::is_sorted(cdf_row.begin(), cdf_row.end())) return;
+    for (int r = 0; r < n; ++r)
+      if (!std::is_sorted(cdf_col.begin() + (size_t)r * n, cdf_col.begin() + (size_t)(r + 1) * n)) return;
+    guide_row.resize(kBokehGuide);
+    guide_col.resize((size_t)n * kBokehGuide);
+    build_guide(cdf_row.data(), n, guide_row.data());
+    for (int r = 0; r < n; ++r) build_guide(cdf_col.data() + (size_t)r * n, n, guide_col.data() + (size_t)r * kBokehGuide);
+  }
   bool build(const lb_bokeh_image *img) {
     if (!img || !img->pixels) return false;
     const int x = img->width, y = img->height, nc = img->channels;
@@ -155,6 +179,7 @@ struct BokehTables {
       prev = 0.f;
       for (int c = 0; c < x; ++c, ++i) prev = cdf_col[i] = prev + per_row[col_idx[i]];
     }
+    build_guides();
     return true;
   }
 };
@@ -190,6 +215,7 @@ struct lb_camera {
   float *d_cdf_row = nullptr, *d_cdf_col = nullptr;
   int32_t *d_row_idx = nullptr, *d_col_idx = nullptr;
   int bokeh_n = 0;
+  bool bokeh_guided = false;  // guide tables present behind d_cdf_row / d_cdf_col
   // host-path pipeline
   cudaStream_t pipe_stream[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t pipe_event[3] = {nullptr, nullptr, nullptr};
@@ -206,6 +232,7 @@ void free_bokeh(lb_camera *c) {
   c->d_cdf_row = c->d_cdf_col = nullptr;
   c->d_row_idx = c->d_col_idx = nullptr;
   c->bokeh_n = 0;
+  c->bokeh_guided = false;
 }
 
 void refresh_consts(lb_camera *c) {
@@ -237,6 +264,9 @@ void refresh_consts(lb_camera *c) {
     k.outer_geom = s.outer_pupil_geometry;
     k.inner_geom = s.inner_pupil_geometry;
     k.cdf_row = c->d_cdf_row; k.row_idx = c->d_row_idx; k.cdf_col = c->d_cdf_col; k.col_idx = c->d_col_idx;
+    const bool guided = k.bokeh_n > 0 && c->bokeh_guided;
+    k.guide_row = guided ? reinterpret_cast<const uint32_t *>(c->d_cdf_row + c->bokeh_n) : nullptr;
+    k.guide_col = guided ? reinterpret_cast<const uint32_t *>(c->d_cdf_col + (size_t)c->bokeh_n * c->bokeh_n) : nullptr;
   };
   fill(c->camf);
   fill(c->camd);
@@ -288,18 +318,19 @@ int camera_setup_impl(lb_camera *c, const lb_camera_params *p, const lb_bokeh_im
 int camera_setup(lb_camera *c, const lb_camera_params *p, const lb_bokeh_image *bokeh) {
   struct Saved {
     lb_camera_params params; lb_camera_state st; LensTable lens; int lens_kernel; CamConsts<float> camf; ThinConsts thin; CamConsts<double> camd;
-    float *cdf_row, *cdf_col; int32_t *row_idx, *col_idx; int bokeh_n;
+    float *cdf_row, *cdf_col; int32_t *row_idx, *col_idx; int bokeh_n; bool bokeh_guided;
   };
-  Saved *old = new Saved{c->params, c->st, c->lens, c->lens_kernel, c->camf, c->thin, c->camd, c->d_cdf_row, c->d_cdf_col, c->d_row_idx, c->d_col_idx, c->bokeh_n};
+  Saved *old = new Saved{c->params, c->st, c->lens, c->lens_kernel, c->camf, c->thin, c->camd, c->d_cdf_row, c->d_cdf_col, c->d_row_idx, c->d_col_idx, c->bokeh_n, c->bokeh_guided};
   // the new tables are built beside the old ones; whichever set loses is freed below
   c->d_cdf_row = c->d_cdf_col = nullptr;
   c->d_row_idx = c->d_col_idx = nullptr;
   c->bokeh_n = 0;
+  c->bokeh_guided = false;
   const int rc = camera_setup_impl(c, p, bokeh);
   if (rc != LB_OK) {
     free_bokeh(c);
     c->params = old->params; c->st = old->st; c->lens = old->lens; c->lens_kernel = old->lens_kernel; c->camf = old->camf; c->thin = old->thin; c->camd = old->camd;
-    c->d_cdf_row = old->cdf_row; c->d_cdf_col = old->cdf_col; c->d_row_idx = old->row_idx; c->d_col_idx = old->col_idx; c->bokeh_n = old->bokeh_n;
+    c->d_cdf_row = old->cdf_row; c->d_cdf_col = old->cdf_col; c->d_row_idx = old->row_idx; c->d_col_idx = old->col_idx; c->bokeh_n = old->bokeh_n; c->bokeh_guided = old->bokeh_guided;
   } else {
     cudaDeviceSynchronize();  // launches that still read the previous tables
     cudaFree(old->cdf_row); cudaFree(old->cdf_col); cudaFree(old->row_idx); cudaFree(old->col_idx);
@@ -342,8 +373,15 @@ int camera_setup_impl(lb_camera *c, const lb_camera_params *p, const lb_bokeh_im
     BokehTables bt;
     if (!bt.build(bokeh)) return fail(LB_ERR_IMAGE, "bokeh image missing, not square or < 3 channels");
     const size_t n = bt.n, n2 = n * n;
-    CU(cudaMalloc(&c->d_cdf_row, n * 4)); CU(cudaMalloc(&c->d_row_idx, n * 4));
-    CU(cudaMalloc(&c->d_cdf_col, n2 * 4)); CU(cudaMalloc(&c->d_col_idx, n2 * 4));
+    // the guide tables ride behind the CDFs in the same allocations
+    const bool guided = !bt.guide_row.empty() && !(getenv("LB_NO_CDF_GUIDE") && getenv("LB_NO_CDF_GUIDE")[0] == '1');
+    CU(cudaMalloc(&c->d_cdf_row, (n + (guided ? kBokehGuide : 0)) * 4)); CU(cudaMalloc(&c->d_row_idx, n * 4));
+    CU(cudaMalloc(&c->d_cdf_col, (n2 + (guided ? n * kBokehGuide : 0)) * 4)); CU(cudaMalloc(&c->d_col_idx, n2 * 4));
+    c->bokeh_guided = guided;
+    if (guided) {
+      CU(cudaMemcpy(c->d_cdf_row + n, bt.guide_row.data(), kBokehGuide * 4, cudaMemcpyHostToDevice));
+      CU(cudaMemcpy(c->d_cdf_col + n2, bt.guide_col.data(), n * kBokehGuide * 4, cudaMemcpyHostToDevice));
+    }
     CU(cudaMemcpy(c->d_cdf_row, bt.cdf_row.data(), n * 4, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(c->d_row_idx, bt.row_idx.data(), n * 4, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(c->d_cdf_col, bt.cdf_col.data(), n2 * 4, cudaMemcpyHostToDevice));
@@ -448,7 +486,7 @@ void lb_camera_params_default(lb_camera_params *p) {  // lentil_camera.cpp:19-52
 int lb_lens_count(void) { return LP_LENS_COUNT; }
 const char *lb_lens_name(int m) { return (m >= 0 && m < LP_LENS_COUNT) ? LP_LENSES[m].name : nullptr; }
 const char *lb_last_error(void) { return g_last_error.c_str(); }
-const char *lb_version(void) { return "lentil_b200 0.3.0 (sm_100a)"; }
+const char *lb_version(void) { return "lentil_b200 0.4.0 (sm_100a)"; }
 
 int lb_camera_create(const lb_camera_params *params, const lb_bokeh_image *bokeh, int device, lb_camera **out) {
   if (!params || !out) return fail(LB_ERR_INVALID, "null argument");

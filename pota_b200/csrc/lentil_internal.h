@@ -90,9 +90,12 @@ struct AovSet {
   float2 *crypto_cache[kMaxAov];     // this batch: [n][max(crypto_depth,1)] merged {id, weight} of each sample, packed,
                                      // kCryptoFree-terminated (cryptomatte_construct_cache, lentil.h:779-811)
   int32_t crypto_slots, crypto_depth;
+  int32_t add_zeros;                 // 1: send all-zero gaussian contributions too (LB_ADD_ZEROS=1, A/B timing); default 0
   unsigned int *work_heads;          // this batch's work list: [0] items appended by classify, [1] next work-unit ticket,
-                                     // [2] sum and [3] maximum of n_samples over the items (classify)
+                                     // [2] sum and [3] maximum of n_samples over the items (classify), [4] the thin-lens
+                                     // splat kernel picked for the batch (k_thinlens_pick); kWorkHeads words
 };
+constexpr int kWorkHeads = 8;
 constexpr uint32_t kCryptoFree = 0xFFFFFFFFu;  // a NaN bit pattern: Cryptomatte hashes are never NaN
 constexpr int kCryptoMaxDepth = 8;
 
@@ -121,6 +124,7 @@ struct FilterCounters {  // device-side mirror of lb_filter_stats
   unsigned long long samples, redistributed, splats, attempts, passthrough;
   unsigned long long newton_its;
   unsigned long long crypto_dropped;
+  unsigned long long tile_splats;  // splats accumulated in a shared-memory window before they reached L2 (thin-lens tile kernel)
 };
 
 cudaError_t launch_filter_classify(const FilterConsts &fc, const AovSet &aovs, const SampleIO &s, WorkItem *work,

@@ -108,6 +108,104 @@ extern "C" int lb_bench_red_peak(int device, int megabytes, double *gbytes_per_s
   return cudaGetLastError() == cudaSuccess ? LB_OK : LB_ERR_CUDA;
 }
 
+// ---- splat accumulate, three ways: what "shared-memory tile accumulation" (north_star) buys on this part ----------------
+// One splat = RGBA (16 B) + filter weight (4 B) added at a pseudo-random pixel.
+//   mode 0: red.global.add.v4.f32 + red.global.add.f32 into planes of `megabytes` MB (what the splat kernels do)
+//   mode 1: shared-memory tile of kTile x kTile pixels, float atomics (ATOMS.CAST.SPIN loops: sm_100a has no native
+//           shared-memory float add), tile flushed once with red.global.add.v4.f32 -- 28 splats per tile pixel
+//   mode 2: the same tile with native 32-bit integer atomics (ATOMS.ADD), i.e. the cost floor of any smem-atomic tile
+namespace {
+constexpr int kTile = 96;  // 96 x 96 x 20 B = 184 KB of the 227 KB a CTA can have
+__global__ void __launch_bounds__(256) k_accum_global(float4 *buf, float *wgt, unsigned npx, int iters) {
+  unsigned s = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
+  const float4 v = make_float4(1.f, 1.f, 1.f, 1.f);
+  for (int i = 0; i < iters; ++i) {
+    s = s * 1664525u + 1013904223u;
+    const unsigned px = (s >> 8) % npx;
+    atomicAdd(buf + px, v);
+    atomicAdd(wgt + px, 1.0f);
+  }
+}
+template <bool kInt>
+__global__ void __launch_bounds__(1024) k_accum_tile(float4 *buf, float *wgt, unsigned npx, int iters) {
+  extern __shared__ float4 tile4[];
+  float *tilew = reinterpret_cast<float *>(tile4 + kTile * kTile);
+  for (int i = threadIdx.x; i < kTile * kTile; i += blockDim.x) { tile4[i] = make_float4(0.f, 0.f, 0.f, 0.f); tilew[i] = 0.f; }
+  __syncthreads();
+  unsigned s = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
+  for (int i = 0; i < iters; ++i) {
+    s = s * 1664525u + 1013904223u;
+    const unsigned px = (s >> 8) % (unsigned)(kTile * kTile);
+    if (kInt) {
+      unsigned *q = reinterpret_cast<unsigned *>(tile4 + px);
+      atomicAdd(q, 1u); atomicAdd(q + 1, 1u); atomicAdd(q + 2, 1u); atomicAdd(q + 3, 1u);
+      atomicAdd(reinterpret_cast<unsigned *>(tilew + px), 1u);
+    } else {
+      float *q = reinterpret_cast<float *>(tile4 + px);
+      atomicAdd(q, 1.f); atomicAdd(q + 1, 1.f); atomicAdd(q + 2, 1.f); atomicAdd(q + 3, 1.f);
+      atomicAdd(tilew + px, 1.f);
+    }
+  }
+  __syncthreads();
+  const unsigned base = (blockIdx.x * 7919u * (unsigned)(kTile * kTile)) % (npx - kTile * kTile);
+  for (int i = threadIdx.x; i < kTile * kTile; i += blockDim.x) {
+    atomicAdd(buf + base + i, tile4[i]);
+    atomicAdd(wgt + base + i, tilew[i]);
+  }
+}
+}  // namespace
+
+// Splats per second (1e9/s) of the accumulate alone; see the modes above.
+extern "C" int lb_bench_splat_accum(int device, int mode, int megabytes, double *gsplats_per_s_out) {
+  if (!gsplats_per_s_out || megabytes <= 0 || mode < 0 || mode > 2) return LB_ERR_INVALID;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device >= ndev) return LB_ERR_NO_DEVICE;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  cudaSetDevice(device);
+  int sms = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  const unsigned npx = (unsigned)((size_t)megabytes * 1000000 / 16);
+  if (npx <= 2u * kTile * kTile) { cudaSetDevice(prev); return LB_ERR_INVALID; }
+  float4 *d = nullptr;
+  float *w = nullptr;
+  if (cudaMalloc(&d, (size_t)npx * 16) != cudaSuccess || cudaMalloc(&w, (size_t)npx * 4) != cudaSuccess) {
+    cudaFree(d);
+    cudaSetDevice(prev);
+    return LB_ERR_CUDA;
+  }
+  cudaMemset(d, 0, (size_t)npx * 16);
+  cudaMemset(w, 0, (size_t)npx * 4);
+  const size_t smem = (size_t)kTile * kTile * 20;
+  cudaFuncSetAttribute(k_accum_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(k_accum_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int iters = 256;
+  const int grid = mode == 0 ? sms * 8 : sms, block = mode == 0 ? 256 : 1024;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(e0);
+    if (mode == 0) k_accum_global<<<grid, block>>>(d, w, npx, iters);
+    else if (mode == 1) k_accum_tile<false><<<grid, block, smem>>>(d, w, npx, iters);
+    else k_accum_tile<true><<<grid, block, smem>>>(d, w, npx, iters);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double g = (double)grid * block * (double)iters / (ms * 1e-3) / 1e9;
+    if (rep > 0 && ms > 0.f && g > best) best = g;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  cudaFree(w);
+  cudaSetDevice(prev);
+  *gsplats_per_s_out = best;
+  return cudaGetLastError() == cudaSuccess ? LB_OK : LB_ERR_CUDA;
+}
+
 // ---- known-answer hooks for the device primitives (tests only; the splat images pin them implicitly) --------------
 #include "lens_device.cuh"
 namespace {

@@ -40,6 +40,9 @@ def main():
     ap.add_argument("--thin", action="store_true")
     ap.add_argument("--skip-k1", action="store_true")
     ap.add_argument("--skip-k2", action="store_true")
+    ap.add_argument("--focus", type=float, default=35.0, help="K2 leg: focus distance (35 = config C3: 144-pixel bokeh discs at 1080p)")
+    ap.add_argument("--disc-radius", type=float, default=0.133, help="K2 leg: radius of the emissive discs (0.133 = config C3)")
+    ap.add_argument("--k2-size", default="1920x1080")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     res = {"tag": a.tag, "lib": os.path.basename(os.environ.get("LB_LIBRARY", "default")), "no_fold": os.environ.get("LB_NO_FOLD", "0"), "lens": a.lens}
@@ -59,11 +62,13 @@ def main():
         cam.close()
         torch.cuda.empty_cache()
     if not a.skip_k2:
-        W, H, spp = 1920, 1080, 16
-        cam = Camera(abi.CameraParams.defaults(camera_type=ctype, lens_model=a.lens, fstop=1.4, focus_dist=35.0, bidir_sample_mult=10,
+        W, H = (int(v) for v in a.k2_size.split("x"))
+        spp = 16
+        res["k2_frame"] = f"{W}x{H}x{spp} focus {a.focus} disc radius {a.disc_radius}"
+        cam = Camera(abi.CameraParams.defaults(camera_type=ctype, lens_model=a.lens, fstop=1.4, focus_dist=a.focus, bidir_sample_mult=10,
                                                bokeh_enable_image=1, focal_length_lentil=50.0),
                      bokeh=workloads.disc_bokeh_image(250), device=0)
-        fr = workloads.highlight_frame(W, H, spp, cam.state.tan_fov, dev, grid=(8, 4))
+        fr = workloads.highlight_frame(W, H, spp, cam.state.tan_fov, dev, grid=(8, 4), radius=a.disc_radius)
         aovs = [("RGBA", abi.LB_FILTER_GAUSSIAN, abi.LB_AOV_RGBA)]
 
         def step():
@@ -97,6 +102,8 @@ def main():
         res["k2_splats_per_s"] = st["splats"] / s
         res["k2_ms"] = s * 1e3
         res["k2_splats"] = st["splats"]
+        res["k2_tile_splats"] = st["tile_splats"]
+        res["k2_redistributed"] = st["redistributed"]
         res["k2_attempts"] = st["attempts"]
         res["k2_its"] = st["newton_its"]
         img = cam.resolve(0)

@@ -27,16 +27,26 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--combine", default="scatter", choices=["scatter", "reduce"])
     ap.add_argument("--tile", type=int, default=4)
+    ap.add_argument("--emulate-world", type=int, default=0, help="single GPU: accumulate rank 0's share of an N-rank run (no combine partner)")
+    ap.add_argument("--order", default="row", choices=["row", "bucket"], help="sample order of a batch: row-major, or 128x128 render buckets")
+    ap.add_argument("--thin", action="store_true", help="ThinLens camera_type instead of PolynomialOptics")
+    ap.add_argument("--tag", default="")
     a = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    p = abi.CameraParams.defaults(camera_type=1, lens_model=5, fstop=1.4, focus_dist=35.0, bidir_sample_mult=10, bokeh_enable_image=1)
+    p = abi.CameraParams.defaults(camera_type=abi.LB_CAMERA_THINLENS if a.thin else abi.LB_CAMERA_POLYNOMIAL_OPTICS, lens_model=5, fstop=1.4,
+                                  focus_dist=35.0, bidir_sample_mult=10, bokeh_enable_image=1, focal_length_lentil=50.0)
     cam = Camera(p, bokeh=workloads.disc_bokeh_image(250), device=local)
     aovs = [("RGBA", 0, 1)] + [(f"light{k}", 0, 0) for k in range(8)] + [("N", 1, 0)]
-    mine = workloads.tile_partition(W, H, a.spp, rank, world, tile=a.tile, device=dev)  # int64 sample indices of this rank
+    part_world = a.emulate_world if (world == 1 and a.emulate_world > 1) else world
+    mine = workloads.tile_partition(W, H, a.spp, rank, part_world, tile=a.tile, device=dev)  # int64 sample indices of this rank
+    if a.order == "bucket":  # as a renderer delivers them: bucket after bucket
+        pix = mine // a.spp
+        key = ((pix // W) // 128) * ((W + 127) // 128) + (pix % W) // 128
+        mine = mine[torch.sort(key, stable=True).indices]
     n_mine = int(mine.numel())
     sizes = torch.zeros(world, dtype=torch.int64, device=dev)
     sizes[rank] = n_mine
@@ -97,7 +107,7 @@ def main():
         splats = float(tsum[3])
         total_ms = float(tmax[0] + tmax[1] + tmax[2])
         block_gb = W * H * (4 * len(aovs) + 1) * 4 / 1e9
-        print("C5 " + json.dumps({"config": f"C5 {W}x{H}x{a.spp}spp, {len(aovs)} AOVs (9 gaussian RGBA + 1 closest), {world} GPU(s)", "combine": a.combine,
+        print("C5 " + json.dumps({"tag": a.tag, "order": a.order, "camera": "thinlens" if a.thin else "po", "emulate_world": a.emulate_world, "config": f"C5 {W}x{H}x{a.spp}spp, {len(aovs)} AOVs (9 gaussian RGBA + 1 closest), {world} GPU(s)", "combine": a.combine,
                           "partition": f"hashed {a.tile}x{a.tile} pixel tiles", "accumulate_ms": float(tmax[0]),
                           "reduce_ms": float(tmax[1]), "resolve_gather_ms": float(tmax[2]), "splats": splats, "splats_per_s": splats / (total_ms * 1e-3),
                           "framebuffer_block_GB": block_gb, "reduce_GBps_per_rank": block_gb / (float(tmax[1]) * 1e-3) if world > 1 else None}))
