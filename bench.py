@@ -588,7 +588,9 @@ def bench_splat(args, rank, world, local_rank, dev, barrier, max_over_ranks, sum
     if world > 1:
         mine = workloads.tile_partition(SPLAT_W, SPLAT_H, spp, rank, world, tile=SPLAT_TILE, device=dev)
         fr = workloads.highlight_frame(SPLAT_W, SPLAT_H, spp, cam.state.tan_fov, dev, grid=SPLAT_GRID, samples=mine)
-        partition = f"hashed {SPLAT_TILE}x{SPLAT_TILE} pixel tiles of source samples over {world} ranks; ncclReduceScatter per plane, per-rank resolve, gather on rank 0"
+        partition = (f"hashed {SPLAT_TILE}x{SPLAT_TILE} pixel tiles of source samples over {world} ranks; " +
+                     ("combine + resolve + gather on rank 0 in one kernel over NVLink peer memory (lb_imager_resolve_peer)"
+                      if os.environ.get("LB_BENCH_COMBINE", "peer") == "peer" else "ncclReduceScatter per plane, per-rank resolve, gather on rank 0"))
     else:
         fr = workloads.highlight_frame(SPLAT_W, SPLAT_H, spp, cam.state.tan_fov, dev, grid=SPLAT_GRID)
         partition = "single GPU: whole frame, no collective"
@@ -601,9 +603,16 @@ def bench_splat(args, rank, world, local_rank, dev, barrier, max_over_ranks, sum
     stream = torch.cuda.current_stream()
     out_img = torch.empty((SPLAT_H, SPLAT_W, 4), dtype=torch.float32, device=dev)
 
+    # N > 1 combine: "peer" = lb_imager_resolve_peer, ONE kernel that sums the ranks' partial planes over NVLink peer memory,
+    # resolves and stores the image on rank 0; "scatter" = ncclReduceScatter + per-rank resolve + ncclSend/Recv gather
+    combine = os.environ.get("LB_BENCH_COMBINE", "peer")
+
     def step():
         cam.filter_begin(SPLAT_W, SPLAT_H, aovs)
         cam.filter_accumulate(fr["px"], fr["py"], fr["rgba"], fr["pos_cs"], 1.0 / spp, stream=stream)
+        if world > 1 and combine == "peer":
+            img = cam.resolve_peer([0], root=0, stream=stream)
+            return None if img is None else img[0]
         if world > 1:
             cam.filter_reduce_scatter(stream=stream)
         return cam.resolve_gather(0, root=0, stream=stream, out=out_img)
@@ -615,9 +624,11 @@ def bench_splat(args, rank, world, local_rank, dev, barrier, max_over_ranks, sum
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(steps):
-        step()
+        last_img = step()
     e1.record(stream)
     barrier()
+    if rank == 0 and last_img is not None:
+        out_img = last_img
     s = max_over_ranks(e0.elapsed_time(e1) * 1e-3) / steps
     st = cam.filter_stats()
     splats = sum_over_ranks(float(st["splats"]))
@@ -648,9 +659,19 @@ def bench_splat(args, rank, world, local_rank, dev, barrier, max_over_ranks, sum
             "red_gbs_per_gpu": red_bytes / s / 1e9 / world, "red_peak_gbs": red_peak.value, "red_frac": red_bytes / s / 1e9 / world / max(red_peak.value, 1e-9),
             "splats_per_step": splats, "attempts_per_step": attempts, "newton_its_per_attempt": its / max(attempts, 1.0),
             "fma_slots_per_newton_trip": slots_per_it}
+    # the accumulate alone, three ways (lb_bench_splat_accum): L2 reductions into L2-resident / HBM-resident planes, and a
+    # shared-memory tile with float atomics -- the evidence behind "the accumulate lives in L2" 
+    if world == 1:
+        v = ctypes.c_double()
+        for key, mode, mb in (("accum_l2_red_gsplats", 0, 41), ("accum_hbm_red_gsplats", 0, 1600), ("accum_smem_tile_cas_gsplats", 1, 41)):
+            if lib().lb_bench_splat_accum(local_rank, mode, mb, ctypes.byref(v)) == 0:
+                flat[key] = v.value
+        flat["accum_note"] = ("1e9 splats/s of the accumulate alone (RGBA + weight, 20 B/splat, random pixels): red.global.add.v4.f32 + .f32 into 41 MB "
+                              "(L2-resident) / 1600 MB planes, and a 96x96 shared-memory tile with float atomics flushed by vector reductions")
     detail = {"metric": "redistributed_splats_per_s", "value": splats / s, "unit": "splats/s", "ms_per_step": s * 1e3, "scaling": "strong",
               "config": {"workload": SPLAT_WORKLOAD, "partition": partition}, "source_samples": total, "image_energy": image_energy,
-              "step": "lb_filter_begin + lb_filter_accumulate (+ lb_filter_reduce_scatter) + lb_imager_resolve_gather"}
+              "step": "lb_filter_begin + lb_filter_accumulate + " + ("lb_imager_resolve_peer (combine + resolve + gather in one kernel over NVLink peer memory)"
+                                                                      if world > 1 and combine == "peer" else "(lb_filter_reduce_scatter +) lb_imager_resolve_gather")}
     # ---- e2e: the same frame with HOST buffers through lb_filter_accumulate_host + lb_imager_resolve_host (N = 1: the path a CPU
     # renderer's filter / imager nodes would drive; at N > 1 every rank feeds its own share and rank 0 reads the gathered image) ----
     e2e = None
@@ -663,10 +684,13 @@ def bench_splat(args, rank, world, local_rank, dev, barrier, max_over_ranks, sum
             cam.filter_begin(SPLAT_W, SPLAT_H, aovs)
             cam.filter_accumulate_host(host["px"], host["py"], host["rgba"], host["pos_cs"], 1.0 / spp)
             if world > 1:
-                cam.filter_reduce_scatter(stream=stream)
-                cam.resolve_gather(0, root=0, stream=stream, out=out_img)
+                if combine == "peer":
+                    img = cam.resolve_peer([0], root=0, stream=stream)
+                else:
+                    cam.filter_reduce_scatter(stream=stream)
+                    img = [cam.resolve_gather(0, root=0, stream=stream, out=out_img)]
                 if rank == 0:
-                    res_dev_host.copy_(out_img, non_blocking=True)
+                    res_dev_host.copy_(img[0], non_blocking=True)
                     stream.synchronize()
             else:
                 cam.resolve_host(0, res)

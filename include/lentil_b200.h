@@ -320,6 +320,22 @@ LB_API int lb_filter_slab(lb_camera *cam, size_t *first_pixel, size_t *n_pixels)
  * ncclAllGather).  rgba_out: device [yres][xres][4], may be NULL on ranks that do not receive.  With a single rank (no
  * communicator) it is a plain full-region resolve. */
 LB_API int lb_imager_resolve_gather(lb_camera *cam, int aov, float *rgba_out, int root, lb_stream stream);
+/* The multi-GPU combine AND driver_process_bucket (lentil_imager.cpp:112-189) in ONE kernel over peer memory (NVLink /
+ * NVSwitch, the ranks' buffers mapped into each other through CUDA IPC): every rank owns one pixel slab of the frame; for its
+ * slab it loads the partial planes of ALL ranks straight from their device memory, sums them in rank order (closest-filter
+ * AOVs: takes the value of the rank that holds the smallest depth key, lentil.h:832-846), resolves, and stores the resolved
+ * pixels into the image block of `root` (of every rank when root < 0).  Replaces lb_filter_reduce_scatter + n x
+ * lb_imager_resolve_gather: no reduced planes are written back, no separate resolve and gather passes, every AOV in one launch.
+ * Collective: every rank of the communicator calls it with the same arguments (ranks must also agree on the frames given to
+ * lb_filter_begin -- the mappings are renewed when buffers are reallocated).  aov_indices: n_out AOVs (no cryptomatte AOVs).
+ * images_out: NULL, or n_out device pointers ([yres][xres][4] floats; entries may be NULL) the receiving ranks copy the
+ * images to; without it they are read in place through lb_imager_peer_image.  The partial planes are left untouched.
+ * At most 8 ranks, world size dividing 5040; single rank / no communicator: a plain resolve of every listed AOV. */
+LB_API int lb_imager_resolve_peer(lb_camera *cam, int n_out, const int *aov_indices, float *const *images_out, int root,
+                                  lb_stream stream);
+/* Device pointer to the [yres][xres][4] image of `aov` that the last lb_imager_resolve_peer left on this (receiving) rank;
+ * valid until the next lb_imager_resolve_peer / lb_filter_begin with another frame size. */
+LB_API int lb_imager_peer_image(lb_camera *cam, int aov, float **image);
 LB_API int lb_comm_destroy(lb_camera *cam);
 
 #ifdef __cplusplus

@@ -30,7 +30,7 @@ EXPORTS = [
     "lb_filter_begin", "lb_filter_accumulate", "lb_filter_accumulate_host", "lb_filter_get_stats",
     "lb_filter_newton_iterations", "lb_imager_resolve", "lb_imager_resolve_host", "lb_filter_buffers", "lb_filter_buffers_host", "lb_filter_crypto_host",
     "lb_bench_fp32_peak", "lb_bench_red_peak", "lb_bench_splat_accum", "lb_camera_set_pupil_geometry", "lb_camera_kernel_kind", "lb_comm_unique_id", "lb_comm_init", "lb_filter_set_sample_base", "lb_filter_reduce", "lb_comm_destroy",
-    "lb_filter_reduce_scatter", "lb_filter_slab", "lb_imager_resolve_gather", "lb_debug_primitives",
+    "lb_filter_reduce_scatter", "lb_filter_slab", "lb_imager_resolve_gather", "lb_debug_primitives", "lb_imager_resolve_peer", "lb_imager_peer_image",
 ]  # fmt: skip
 
 
@@ -84,6 +84,8 @@ def lib():
         L.lb_filter_reduce_scatter.argtypes = [vp, vp]
         L.lb_filter_slab.argtypes = [vp, C.POINTER(sz), C.POINTER(sz)]
         L.lb_imager_resolve_gather.argtypes = [vp, i, vp, i, vp]
+        L.lb_imager_resolve_peer.argtypes = [vp, i, C.POINTER(C.c_int), C.POINTER(vp), i, vp]
+        L.lb_imager_peer_image.argtypes = [vp, i, C.POINTER(vp)]
         L.lb_debug_primitives.argtypes = [i, sz, vp, vp, vp, vp, vp, vp]
         _lib = L
     return _lib
@@ -136,6 +138,7 @@ class Camera:
         self._frame = None
         self._aovs = []
         self._rank = 0
+        self._world = 1
 
     def close(self):
         if getattr(self, "_h", None):
@@ -322,6 +325,7 @@ class Camera:
     def comm_init(self, world_size: int, rank: int, unique_id: bytes):
         _check(lib().lb_comm_init(self._h, world_size, rank, unique_id))
         self._rank = rank
+        self._world = world_size
 
     def filter_set_sample_base(self, base: int):
         _check(lib().lb_filter_set_sample_base(self._h, base))
@@ -350,6 +354,29 @@ class Camera:
             out = torch.empty((f.yres, f.xres, 4), dtype=torch.float32, device=f"cuda:{self.device}")
         _check(lib().lb_imager_resolve_gather(self._h, aov, _dptr(out), root, _stream_ptr(stream)))
         return out if rank_gets else None
+
+    def resolve_peer(self, aovs, root: int = 0, stream=None, copy: bool = False):
+        """lb_imager_resolve_peer: combine + resolve of the listed AOVs in one kernel over peer memory (collective).  Returns the
+        [yres, xres, 4] device tensors on the receiving ranks (views of the library's image block unless copy=True), None elsewhere."""
+        import torch
+
+        f = self._frame
+        aovs = list(aovs)
+        idx = (C.c_int * len(aovs))(*aovs)
+        _check(lib().lb_imager_resolve_peer(self._h, len(aovs), idx, None, root, _stream_ptr(stream)))
+        if not (root < 0 or self._rank == root or self._world == 1):
+            return None
+        outs = []
+        for a in aovs:
+            ptr = C.c_void_p()
+            _check(lib().lb_imager_peer_image(self._h, a, C.byref(ptr)))
+
+            class _View:  # zero-copy: the image stays in the library's block
+                __cuda_array_interface__ = {"shape": (f.yres, f.xres, 4), "typestr": "<f4", "data": (ptr.value, False), "version": 2}
+
+            t = torch.as_tensor(_View(), device=f"cuda:{self.device}")
+            outs.append(t.clone() if copy else t)
+        return outs
 
     def comm_destroy(self):
         _check(lib().lb_comm_destroy(self._h))

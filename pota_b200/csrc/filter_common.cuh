@@ -70,7 +70,7 @@ LB_DEV void crypto_insert(uint32_t *__restrict__ keys, float *__restrict__ wgts,
 LB_DEV void crypto_add(const AovSet &aovs, int a, size_t i, bool on, unsigned pixel, float sample_weight, FilterCounters *counters) {
   const int stride = aovs.crypto_depth > 1 ? aovs.crypto_depth : 1;
   const float2 *e = aovs.crypto_cache[a] + i * (size_t)stride;
-  if (on) atomicAdd(&aovs.buffer[a][pixel].x, sample_weight);  // crypto_total_weight
+  if (on && a == aovs.crypto_first) atomicAdd(&aovs.buffer[a][pixel].x, sample_weight);  // crypto_total_weight, one plane for every cryptomatte AOV
   for (int j = 0; j < stride; ++j) {
     const float2 kv = e[j];
     if (__float_as_uint(kv.x) == kCryptoFree) break;

@@ -94,6 +94,17 @@ struct FilterState {
   // NCCL
   ncclComm_t comm = nullptr;
   int world = 1, rank = 0;
+  // peer-memory combine (lb_imager_resolve_peer): every rank maps the other ranks' planes, depth keys and image block through
+  // CUDA IPC; alloc_gen counts (re)allocations of the exported buffers, peer_gen is the generation the mappings belong to
+  static constexpr int kMaxPeers = 8;
+  uint64_t alloc_gen = 1, peer_gen = 0;
+  float *peer_block[kMaxPeers] = {};
+  unsigned long long *peer_zkey[kMaxPeers] = {}, *peer_zkey_debug[kMaxPeers] = {};
+  float4 *peer_img[kMaxPeers] = {};
+  float4 *img_block = nullptr;   // [n_aov][npx_pad] resolved images, written by the owners of the slabs (this rank's own mapping)
+  size_t img_floats = 0;
+  float *barrier_word = nullptr; // 4-byte all-reduce = stream-ordered barrier across the ranks
+  unsigned char *ipc_dev = nullptr;  // [world][kIpcBytes] handle exchange
 };
 namespace lb { FilterState *&cam_filter(lb_camera *c); }
 
@@ -152,6 +163,30 @@ NcclApi *load_nccl() {
   return (api.h && api.GetUniqueId && api.CommInitRank && api.AllReduce && api.Reduce) ? &api : nullptr;
 }
 
+// Unmap every peer buffer, then wait until all ranks have done the same (the owner may only free an exported buffer after
+// its importers have closed it).  Collective when mappings exist; a no-op otherwise.
+int peer_release(FilterState *f) {
+  if (f->peer_gen == 0) return LB_OK;
+  for (int r = 0; r < FilterState::kMaxPeers; ++r) {
+    if (r != f->rank) {
+      if (f->peer_block[r]) cudaIpcCloseMemHandle(f->peer_block[r]);
+      if (f->peer_zkey[r]) cudaIpcCloseMemHandle(f->peer_zkey[r]);
+      if (f->peer_zkey_debug[r]) cudaIpcCloseMemHandle(f->peer_zkey_debug[r]);
+      if (f->peer_img[r]) cudaIpcCloseMemHandle(f->peer_img[r]);
+    }
+    f->peer_block[r] = nullptr; f->peer_zkey[r] = f->peer_zkey_debug[r] = nullptr; f->peer_img[r] = nullptr;
+  }
+  cudaGetLastError();
+  f->peer_gen = 0;
+  NcclApi *n = load_nccl();
+  if (n && f->comm && f->barrier_word && f->stream) {
+    if (n->AllReduce(f->barrier_word, f->barrier_word + 1, 1, ncclFloat32, ncclSum, f->comm, f->stream) != ncclSuccess)
+      return lb_fail(LB_ERR_COMM, "barrier before releasing peer-mapped buffers failed");
+    CUF(cudaStreamSynchronize(f->stream));
+  }
+  return LB_OK;
+}
+
 void fill_consts(lb_camera *c, const FilterState *f, FilterConsts &fc) {
   const lb_camera_params &p = cam_params(c);
   const lb_camera_state &s = cam_state(c);
@@ -181,15 +216,28 @@ void fill_consts(lb_camera *c, const FilterState *f, FilterConsts &fc) {
   fc.aspect_full = (double)f->frame.xres_without_region / (double)f->frame.yres_without_region;
 }
 
+// The plane an AOV's per-pixel floats live in.  AOVData::crypto_total_weight (lentil.h:815) receives the same `sample_weight`
+// for every cryptomatte AOV of the frame (lentil_filter.cpp:295-298 calls add_to_buffer for each of them per splat), so ONE
+// plane -- the first cryptomatte AOV's -- holds it for all of them: one reduction per splat instead of one per cryptomatte AOV.
+int plane_of(const FilterState *f, int aov) {
+  if (f->crypto_of[aov] < 0) return aov;
+  for (int a = 0; a < f->n_aov; ++a)
+    if (f->crypto_of[a] >= 0) return a;
+  return aov;
+}
+
 void fill_aovs(const FilterState *f, AovSet &A, const lb_samples *S, const FilterState::Scratch *sc) {
   memset(&A, 0, sizeof A);
   const float *const *values = S ? S->aov_values : nullptr;
   A.crypto_slots = f->crypto_slots;
+  A.crypto_first = -1;
+  for (int a = f->n_aov - 1; a >= 0; --a)
+    if (f->crypto_of[a] >= 0) A.crypto_first = a;
   A.crypto_depth = S ? S->crypto_depth : 0;
   const bool add_zeros = getenv("LB_ADD_ZEROS") && getenv("LB_ADD_ZEROS")[0] == '1';
   A.add_zeros = add_zeros ? 1 : 0;
   for (int a = 0; a < f->n_aov; ++a) {
-    A.buffer[a] = (float4 *)(f->block + (size_t)a * f->npx_pad * 4);
+    A.buffer[a] = (float4 *)(f->block + (size_t)plane_of(f, a) * f->npx_pad * 4);
     A.values[a] = values ? (const float4 *)values[a] : nullptr;
     A.filter[a] = f->aovs[a].filter;
     A.role[a] = f->aovs[a].role;
@@ -301,12 +349,16 @@ __global__ void k_mask_closest(const unsigned long long *__restrict__ local_key,
 
 void filter_state_destroy(FilterState *f) {
   if (!f) return;
+  peer_release(f);
   if (f->comm) { if (NcclApi *n = load_nccl()) n->CommDestroy(f->comm); }
+  f->comm = nullptr;
   cudaFree(f->block); cudaFree(f->zkey); cudaFree(f->zkey_debug);
   for (auto &sc : f->scratch) {
     cudaFree(sc.work); cudaFree(sc.debug_samples); cudaFree(sc.crypto_cache); cudaFree(sc.heads);
     if (sc.done) cudaEventDestroy(sc.done);
   }
+  peer_release(f);  // (lb_comm_destroy has normally done it, with the barrier)
+  cudaFree(f->img_block); cudaFree(f->barrier_word); cudaFree(f->ipc_dev);
   cudaFree(f->crypto_tables);
   cudaFree(f->d_counters); cudaFree(f->gather); cudaFree(f->res_dev); cudaFree(f->brk_dev);
   for (int a = 0; a < kMaxAov; ++a) { cudaFreeHost(f->res_host[a]); cudaFreeHost(f->brk_host[a]); }
@@ -345,11 +397,16 @@ int lb_filter_begin(lb_camera *c, const lb_frame_desc *frame, int n_aov, const l
   const size_t npx_pad = (npx + kSlabAlign - 1) / kSlabAlign * kSlabAlign;
   const size_t floats = npx_pad * (4 * (size_t)n_aov + 1);
   // destroy_buffers + reallocate (lentil.h:214,1096-1117).  cudaFree waits for work in flight on the old buffers.
+  if (floats != f->block_floats || npx != f->zkey_npx) {  // buffers other ranks have mapped (lb_imager_resolve_peer): unmapped everywhere first
+    const int rcp = peer_release(f);
+    if (rcp != LB_OK) return rcp;
+  }
   if (floats != f->block_floats) {
     cudaFree(f->block);
     f->block = nullptr; f->block_floats = 0;
     CUF(cudaMalloc(&f->block, floats * sizeof(float)));
     f->block_floats = floats;
+    ++f->alloc_gen;
   }
   if (npx != f->zkey_npx) {  // sized by the pixel count alone: two frames can share `floats` and differ in npx
     cudaFree(f->zkey); cudaFree(f->zkey_debug); cudaFree(f->gather);
@@ -357,6 +414,7 @@ int lb_filter_begin(lb_camera *c, const lb_frame_desc *frame, int n_aov, const l
     CUF(cudaMalloc(&f->zkey, npx * sizeof(unsigned long long)));
     CUF(cudaMalloc(&f->zkey_debug, npx * sizeof(unsigned long long)));
     f->zkey_npx = npx;
+    ++f->alloc_gen;
   }
   f->npx = npx;
   f->npx_pad = npx_pad;
@@ -553,7 +611,7 @@ int lb_imager_resolve(lb_camera *c, int aov, int x0, int y0, int w, int h, float
   { const int rcw = wait_all_accumulates(f, stream); if (rcw != LB_OK) return rcw; }
   if (f->crypto_of[aov] >= 0) {
     const uint32_t *key = f->crypto_tables + (size_t)f->crypto_of[aov] * f->crypto_table_words;
-    CUF(launch_resolve_crypto(key, (const float *)(key + f->crypto_table_words / 2), (const float4 *)(f->block + (size_t)aov * f->npx_pad * 4),
+    CUF(launch_resolve_crypto(key, (const float *)(key + f->crypto_table_words / 2), (const float4 *)(f->block + (size_t)plane_of(f, aov) * f->npx_pad * 4),
                               f->crypto_slots, f->crypto_rank[aov], f->frame.xres, rx, ry, w, h, (float4 *)rgba_out, nullptr, stream));
   } else {
     CUF(launch_resolve((const float4 *)(f->block + (size_t)aov * f->npx_pad * 4), f->block + (size_t)f->n_aov * f->npx_pad * 4, f->aovs[aov].filter,
@@ -601,7 +659,7 @@ int lb_imager_resolve_host(lb_camera *c, int aov, int x0, int y0, int w, int h, 
     if (crypto) {
       const uint32_t *key = f->crypto_tables + (size_t)f->crypto_of[aov] * f->crypto_table_words;
       CUF(cudaMemsetAsync(f->res_dev, 0, f->npx * sizeof(float4), st));
-      CUF(launch_resolve_crypto(key, (const float *)(key + f->crypto_table_words / 2), (const float4 *)(f->block + (size_t)aov * f->npx_pad * 4),
+      CUF(launch_resolve_crypto(key, (const float *)(key + f->crypto_table_words / 2), (const float4 *)(f->block + (size_t)plane_of(f, aov) * f->npx_pad * 4),
                                 f->crypto_slots, f->crypto_rank[aov], xr, 0, 0, xr, yr, f->res_dev, f->brk_dev, st));
       CUF(cudaMemcpyAsync(f->brk_host[aov], f->brk_dev, f->npx, cudaMemcpyDeviceToHost, st));
     } else {
@@ -631,7 +689,7 @@ int lb_filter_buffers(lb_camera *c, int aov, float **buffer, float **weight) {
   FilterState *f = c ? cam_filter(c) : nullptr;
   if (!f) return lb_fail(LB_ERR_STATE, "lb_filter_begin has not been called");
   if (aov < 0 || aov >= f->n_aov) return lb_fail(LB_ERR_INVALID, "aov index out of range");
-  if (buffer) *buffer = f->block + (size_t)aov * f->npx_pad * 4;
+  if (buffer) *buffer = f->block + (size_t)plane_of(f, aov) * f->npx_pad * 4;
   if (weight) *weight = f->block + (size_t)f->n_aov * f->npx_pad * 4;
   return LB_OK;
 }
@@ -642,7 +700,7 @@ int lb_filter_buffers_host(lb_camera *c, int aov, float *buffer_out, float *weig
   if (aov < 0 || aov >= f->n_aov) return lb_fail(LB_ERR_INVALID, "aov index out of range");
   DeviceGuard g(cam_device(c));
   CUF(cudaDeviceSynchronize());
-  if (buffer_out) CUF(cudaMemcpy(buffer_out, f->block + (size_t)aov * f->npx_pad * 4, f->npx * 16, cudaMemcpyDeviceToHost));
+  if (buffer_out) CUF(cudaMemcpy(buffer_out, f->block + (size_t)plane_of(f, aov) * f->npx_pad * 4, f->npx * 16, cudaMemcpyDeviceToHost));
   if (weight_out) CUF(cudaMemcpy(weight_out, f->block + (size_t)f->n_aov * f->npx_pad * 4, f->npx * 4, cudaMemcpyDeviceToHost));
   return LB_OK;
 }
@@ -677,7 +735,7 @@ int lb_comm_init(lb_camera *c, int world_size, int rank, const uint8_t id_in[128
   NcclApi *n = load_nccl();
   if (!n) return lb_fail(LB_ERR_COMM, "libnccl.so.2 not found (set LB_NCCL_LIB)");
   DeviceGuard g(cam_device(c));
-  if (f->comm) { n->CommDestroy(f->comm); f->comm = nullptr; }
+  if (f->comm) { peer_release(f); n->CommDestroy(f->comm); f->comm = nullptr; }
   ncclUniqueId id;
   memcpy(id.internal, id_in, 128);
   ncclResult_t r = n->CommInitRank(&f->comm, world_size, id, rank);
@@ -855,9 +913,194 @@ int lb_imager_resolve_gather(lb_camera *c, int aov, float *rgba_out, int root, l
 int lb_comm_destroy(lb_camera *c) {
   FilterState *f = c ? cam_filter(c) : nullptr;
   if (!f || !f->comm) return LB_OK;
+  peer_release(f);
   if (NcclApi *n = load_nccl()) n->CommDestroy(f->comm);
   f->comm = nullptr;
   f->world = 1;
+  return LB_OK;
+}
+
+}  // extern "C"
+
+// ---- multi-GPU combine + resolve in ONE kernel over peer memory ------------------------------------------------------
+namespace {
+struct PeerSet {
+  const float *block[FilterState::kMaxPeers];                    // every rank's [n_aov][npx_pad] float4 planes + [npx_pad] weight plane
+  const unsigned long long *zkey[FilterState::kMaxPeers];        // every rank's depth keys (closest-filter AOVs)
+  const unsigned long long *zkey_debug[FilterState::kMaxPeers];
+  float4 *img[FilterState::kMaxPeers];                           // every rank's image block [n_aov][npx_pad]
+  int world, root, n_aov, n_out;
+  int out_aov[kMaxAov], filter[kMaxAov], role[kMaxAov];
+  size_t npx_pad;
+};
+
+// driver_process_bucket (lentil_imager.cpp:112-189) for the pixels [lo, lo + cnt) this rank owns, reading the partial
+// framebuffers of ALL ranks through NVLink: gaussian AOVs are summed in rank order and divided by the summed filter weight,
+// closest-filter AOVs take the value of the rank whose depth key is smallest (what the sequential z-test keeps,
+// lentil.h:832-846).  The resolved pixel goes straight into the image block of `root` (of every rank when root < 0).
+// Loads are 16 B and independent across ranks and AOVs (world x (n_out + 1) in flight per thread); stores are coalesced
+// 512 B per warp.  Bound: the NVLink ingress of the slab owner, (world - 1) / world of the planes.
+__global__ void __launch_bounds__(256) k_resolve_peer(const __grid_constant__ PeerSet P, size_t lo, size_t cnt) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t p = lo + i;
+    float fw = 0.f;
+    for (int r = 0; r < P.world; ++r) fw += __ldcs(P.block[r] + (size_t)P.n_aov * P.npx_pad * 4 + p);
+    for (int k = 0; k < P.n_out; ++k) {
+      const int a = P.out_aov[k];
+      const size_t at = (size_t)a * P.npx_pad + p;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (P.filter[a] == 0) {
+        for (int r = 0; r < P.world; ++r) {
+          const float4 t = __ldcs(reinterpret_cast<const float4 *>(P.block[r]) + at);
+          v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+        }
+        if (P.role[a] != 2 && fw != 0.0f) { const float inv = 1.0f / fw; v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv; }
+      } else {
+        unsigned long long best = ~0ull;
+        int who = 0;
+        for (int r = 0; r < P.world; ++r) {
+          const unsigned long long key = __ldcs((P.role[a] == 2 ? P.zkey_debug[r] : P.zkey[r]) + p);
+          if (key < best) { best = key; who = r; }
+        }
+        if (best != ~0ull) v = __ldcs(reinterpret_cast<const float4 *>(P.block[who]) + at);
+        v.w = 1.0f;
+      }
+      if (P.root >= 0) P.img[P.root][at] = v;
+      else
+        for (int r = 0; r < P.world; ++r) P.img[r][at] = v;
+    }
+  }
+  __threadfence_system();
+}
+
+constexpr size_t kIpcBytes = 4 * sizeof(cudaIpcMemHandle_t) + 8;
+
+// (re)map the peers' buffers: handles travel through a device buffer and ncclAllGather
+int peer_exchange(FilterState *f, NcclApi *n, cudaStream_t stream) {
+  auto check = [&](ncclResult_t r) { return r == ncclSuccess ? LB_OK : lb_fail(LB_ERR_COMM, n->GetErrorString ? n->GetErrorString(r) : "nccl error"); };
+  if (!f->barrier_word) { CUF(cudaMalloc(&f->barrier_word, 8)); CUF(cudaMemset(f->barrier_word, 0, 8)); }
+  const size_t want_img = (size_t)f->n_aov * f->npx_pad * 4;
+  if (f->img_floats != want_img) {  // (the ranks agree on the frame, so they all take this branch together)
+    const int rcp = peer_release(f);
+    if (rcp != LB_OK) return rcp;
+    cudaFree(f->img_block);
+    f->img_block = nullptr; f->img_floats = 0;
+    CUF(cudaMalloc(&f->img_block, want_img * sizeof(float)));
+    f->img_floats = want_img;
+    ++f->alloc_gen;
+  }
+  if (f->peer_gen == f->alloc_gen) return LB_OK;
+  { const int rcp = peer_release(f); if (rcp != LB_OK) return rcp; }
+  if (!f->ipc_dev) CUF(cudaMalloc(&f->ipc_dev, FilterState::kMaxPeers * kIpcBytes));
+  unsigned char mine[kIpcBytes];
+  memset(mine, 0, sizeof mine);
+  void *bufs[4] = {f->block, f->zkey, f->zkey_debug, f->img_block};
+  for (int k = 0; k < 4; ++k) {
+    cudaIpcMemHandle_t h;
+    CUF(cudaIpcGetMemHandle(&h, bufs[k]));
+    memcpy(mine + k * sizeof h, &h, sizeof h);
+  }
+  CUF(cudaMemcpyAsync(f->ipc_dev + (size_t)f->rank * kIpcBytes, mine, kIpcBytes, cudaMemcpyHostToDevice, stream));
+  int rc = check(n->AllGather(f->ipc_dev + (size_t)f->rank * kIpcBytes, f->ipc_dev, kIpcBytes, ncclInt8, f->comm, stream));
+  if (rc != LB_OK) return rc;
+  std::vector<unsigned char> all((size_t)f->world * kIpcBytes);
+  CUF(cudaMemcpyAsync(all.data(), f->ipc_dev, all.size(), cudaMemcpyDeviceToHost, stream));
+  CUF(cudaStreamSynchronize(stream));
+  for (int r = 0; r < f->world; ++r) {
+    if (r == f->rank) {
+      f->peer_block[r] = f->block; f->peer_zkey[r] = f->zkey; f->peer_zkey_debug[r] = f->zkey_debug; f->peer_img[r] = f->img_block;
+      continue;
+    }
+    void *ptr[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (int k = 0; k < 4; ++k) {
+      cudaIpcMemHandle_t h;
+      memcpy(&h, all.data() + (size_t)r * kIpcBytes + k * sizeof h, sizeof h);
+      const cudaError_t e = cudaIpcOpenMemHandle(&ptr[k], h, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) return lb_fail(LB_ERR_COMM, "cudaIpcOpenMemHandle failed (no peer access between the ranks' devices?): use lb_filter_reduce_scatter");
+    }
+    f->peer_block[r] = (float *)ptr[0]; f->peer_zkey[r] = (unsigned long long *)ptr[1];
+    f->peer_zkey_debug[r] = (unsigned long long *)ptr[2]; f->peer_img[r] = (float4 *)ptr[3];
+  }
+  f->peer_gen = f->alloc_gen;
+  return LB_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int lb_imager_resolve_peer(lb_camera *c, int n_out, const int *aov_indices, float *const *images_out, int root, lb_stream stream_) {
+  FilterState *f = c ? cam_filter(c) : nullptr;
+  if (!f) return lb_fail(LB_ERR_STATE, "lb_filter_begin has not been called");
+  if (n_out <= 0 || n_out > f->n_aov || !aov_indices) return lb_fail(LB_ERR_INVALID, "bad AOV list");
+  if (root >= f->world) return lb_fail(LB_ERR_INVALID, "root out of range");
+  for (int k = 0; k < n_out; ++k) {
+    if (aov_indices[k] < 0 || aov_indices[k] >= f->n_aov) return lb_fail(LB_ERR_INVALID, "aov index out of range");
+    if (f->crypto_of[aov_indices[k]] >= 0) return lb_fail(LB_ERR_INVALID, "cryptomatte AOVs combine with lb_filter_reduce (id tables are merged, not summed)");
+  }
+  if (f->world > FilterState::kMaxPeers) return lb_fail(LB_ERR_INVALID, "more than 8 ranks: use lb_filter_reduce_scatter");
+  if (f->npx_pad % (size_t)f->world) return lb_fail(LB_ERR_INVALID, "world size does not divide the plane granule (5040): use lb_filter_reduce");
+  if (f->scattered) return lb_fail(LB_ERR_STATE, "lb_filter_reduce_scatter has already consumed this frame's partial planes");
+  std::lock_guard<std::mutex> lk(cam_mutex(c));
+  DeviceGuard g(cam_device(c));
+  cudaStream_t stream = (cudaStream_t)stream_;
+  { const int rcw = wait_all_accumulates(f, stream); if (rcw != LB_OK) return rcw; }
+  const bool single = f->world <= 1 || !f->comm;
+  NcclApi *n = single ? nullptr : load_nccl();
+  if (!single && (!n || !n->AllGather)) return lb_fail(LB_ERR_COMM, "NCCL unavailable");
+  auto check = [&](ncclResult_t r) { return r == ncclSuccess ? LB_OK : lb_fail(LB_ERR_COMM, n->GetErrorString ? n->GetErrorString(r) : "nccl error"); };
+  int rc = LB_OK;
+  if (single) {
+    const size_t want_img = (size_t)f->n_aov * f->npx_pad * 4;
+    if (f->img_floats != want_img) {
+      cudaFree(f->img_block);
+      f->img_block = nullptr; f->img_floats = 0;
+      CUF(cudaMalloc(&f->img_block, want_img * sizeof(float)));
+      f->img_floats = want_img;
+    }
+  } else if ((rc = peer_exchange(f, n, stream)) != LB_OK) {
+    return rc;
+  }
+  PeerSet P;
+  memset(&P, 0, sizeof P);
+  P.world = single ? 1 : f->world;
+  P.root = single ? 0 : root;
+  P.n_aov = f->n_aov;
+  P.n_out = n_out;
+  P.npx_pad = f->npx_pad;
+  for (int k = 0; k < n_out; ++k) P.out_aov[k] = aov_indices[k];
+  for (int a = 0; a < f->n_aov; ++a) { P.filter[a] = f->aovs[a].filter; P.role[a] = f->aovs[a].role; }
+  for (int r = 0; r < P.world; ++r) {
+    P.block[r] = single ? f->block : f->peer_block[r];
+    P.zkey[r] = single ? f->zkey : f->peer_zkey[r];
+    P.zkey_debug[r] = single ? f->zkey_debug : f->peer_zkey_debug[r];
+    P.img[r] = single ? f->img_block : f->peer_img[r];
+  }
+  // barrier: every rank's accumulates have finished (and nobody still reads the previous frame's images) before any rank loads
+  if (!single && (rc = check(n->AllReduce(f->barrier_word, f->barrier_word + 1, 1, ncclFloat32, ncclSum, f->comm, stream))) != LB_OK) return rc;
+  const size_t slab = f->npx_pad / (size_t)P.world;
+  const size_t lo = single ? 0 : (size_t)f->rank * slab;
+  const size_t cnt = lo < f->npx ? std::min(slab, f->npx - lo) : 0;
+  if (cnt) {
+    const unsigned grid = (unsigned)std::min<size_t>((cnt + 255) / 256, (size_t)cam_num_sms(c) * 16);
+    k_resolve_peer<<<grid, 256, 0, stream>>>(P, lo, cnt);
+    CUF(cudaGetLastError());
+  }
+  // barrier: every owner has stored its slab before the images are read, and before the next lb_filter_begin zeroes the planes
+  if (!single && (rc = check(n->AllReduce(f->barrier_word, f->barrier_word + 1, 1, ncclFloat32, ncclSum, f->comm, stream))) != LB_OK) return rc;
+  const bool mine = single || root < 0 || root == f->rank;
+  if (mine && images_out)
+    for (int k = 0; k < n_out; ++k)
+      if (images_out[k])
+        CUF(cudaMemcpyAsync(images_out[k], f->img_block + (size_t)aov_indices[k] * f->npx_pad, f->npx * sizeof(float4), cudaMemcpyDeviceToDevice, stream));
+  CUF(cudaEventRecord(f->ev_done, stream));
+  return LB_OK;
+}
+
+int lb_imager_peer_image(lb_camera *c, int aov, float **image) {
+  FilterState *f = c ? cam_filter(c) : nullptr;
+  if (!f || !f->img_block) return lb_fail(LB_ERR_STATE, "lb_imager_resolve_peer has not been called");
+  if (aov < 0 || aov >= f->n_aov || !image) return lb_fail(LB_ERR_INVALID, "bad arguments");
+  *image = reinterpret_cast<float *>(f->img_block + (size_t)aov * f->npx_pad);
   return LB_OK;
 }
 

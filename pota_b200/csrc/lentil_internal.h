@@ -90,6 +90,7 @@ struct AovSet {
   float2 *crypto_cache[kMaxAov];     // this batch: [n][max(crypto_depth,1)] merged {id, weight} of each sample, packed,
                                      // kCryptoFree-terminated (cryptomatte_construct_cache, lentil.h:779-811)
   int32_t crypto_slots, crypto_depth;
+  int32_t crypto_first;              // the cryptomatte AOV whose plane holds crypto_total_weight for all of them (-1: none)
   int32_t add_zeros;                 // 1: send all-zero gaussian contributions too (LB_ADD_ZEROS=1, A/B timing); default 0
   unsigned int *work_heads;          // this batch's work list: [0] items appended by classify, [1] next work-unit ticket,
                                      // [2] sum and [3] maximum of n_samples over the items (classify), [4] the thin-lens

@@ -25,7 +25,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--spp", type=int, default=16)
     ap.add_argument("--steps", type=int, default=2)
-    ap.add_argument("--combine", default="scatter", choices=["scatter", "reduce"])
+    ap.add_argument("--combine", default="peer", choices=["peer", "scatter", "reduce"])
     ap.add_argument("--tile", type=int, default=4)
     ap.add_argument("--emulate-world", type=int, default=0, help="single GPU: accumulate rank 0's share of an N-rank run (no combine partner)")
     ap.add_argument("--order", default="row", choices=["row", "bucket"], help="sample order of a batch: row-major, or 128x128 render buckets")
@@ -81,7 +81,10 @@ def main():
         if world > 1:
             dist.barrier()
         e0.record(stream)
-        if a.combine == "scatter":
+        if a.combine == "peer":  # one kernel: sum over NVLink peer memory + resolve + store on rank 0, all AOVs
+            e1.record(stream)
+            imgs = cam.resolve_peer(range(len(aovs)), root=0, stream=stream)
+        elif a.combine == "scatter":
             cam.filter_reduce_scatter(stream=stream)
             e1.record(stream)
             out = torch.empty((H, W, 4), dtype=torch.float32, device=dev) if rank == 0 else None

@@ -91,6 +91,48 @@ def main():
     cam.filter_begin(W, H, aovs2)
     cam.filter_set_sample_base(base)
     cam.filter_accumulate(fr2["px"], fr2["py"], fr2["rgba"], fr2["pos_cs"], 1.0 / spp, aov_values=[None, fr2["aov_values"][0], fr2["aov_values"][1], fr2["rgba"]])
+    # the fused combine + resolve over peer memory runs on the untouched partial planes, before the reduce-scatter consumes them
+    single2 = Camera(p, device=local)
+    run2(single2, torch.cat(shares))
+    want2 = [single2.resolve(a).cpu().numpy() for a in range(len(aovs2))]
+    for root in (0, -1, world - 1):
+        for rep in range(2):  # twice: the second call reuses the peer mappings
+            imgs = cam.resolve_peer(range(len(aovs2)), root=root, copy=True)
+        torch.cuda.synchronize()
+        if root < 0 or rank == root:
+            for a, (name, flt, role) in enumerate(aovs2):
+                got = imgs[a].cpu().numpy()
+                if flt == 0:
+                    np.testing.assert_allclose(got, want2[a], rtol=1e-4, atol=2e-5, err_msg=f"resolve_peer root={root} {name}")
+                else:
+                    assert (np.abs(got - want2[a]).max(axis=2) > 1e-6).mean() < 1e-3, f"resolve_peer root={root} closest {name}"
+        else:
+            assert imgs is None
+    # a frame of another size: buffers are reallocated on every rank, the mappings renewed
+    W3, H3 = 256, 144
+    shares3 = [workloads.tile_partition(W3, H3, spp, r, world, tile=16, device=dev) for r in range(world)]
+    cam3_aovs = [("RGBA", 0, 1), ("N", 1, 0)]
+
+    def run3(c, k, base):
+        fr = workloads.highlight_frame(W3, H3, spp, c.state.tan_fov, dev, samples=k)
+        c.filter_begin(W3, H3, cam3_aovs)
+        c.filter_set_sample_base(base)
+        c.filter_accumulate(fr["px"], fr["py"], fr["rgba"], fr["pos_cs"], 1.0 / spp, aov_values=[None, fr["rgba"]])
+        return fr
+
+    keep3 = run3(cam, shares3[rank], sum(int(s.numel()) for s in shares3[:rank]))
+    imgs3 = cam.resolve_peer([0, 1], root=0)
+    torch.cuda.synchronize()
+    if rank == 0:
+        single3 = Camera(p, device=local)
+        run3(single3, torch.cat(shares3), 0)
+        np.testing.assert_allclose(imgs3[0].cpu().numpy(), single3.resolve(0).cpu().numpy(), rtol=1e-4, atol=2e-5, err_msg="resolve_peer after a frame-size change")
+        assert (np.abs(imgs3[1].cpu().numpy() - single3.resolve(1).cpu().numpy()).max(axis=2) > 1e-6).mean() < 1e-3
+    dist.barrier()
+    # back to the first frame for the reduce-scatter path
+    cam.filter_begin(W, H, aovs2)
+    cam.filter_set_sample_base(base)
+    cam.filter_accumulate(fr2["px"], fr2["py"], fr2["rgba"], fr2["pos_cs"], 1.0 / spp, aov_values=[None, fr2["aov_values"][0], fr2["aov_values"][1], fr2["rgba"]])
     cam.filter_reduce_scatter()
     lo_px, n_px = cam.filter_slab()
     assert n_px > 0 and (rank > 0 or lo_px == 0)
@@ -117,7 +159,7 @@ def main():
     dist.barrier()
     cam.comm_destroy()
     if rank == 0:
-        print(f"multi_gpu_check ok: world={world}, {total} samples, reduce + all-reduce + reduce-scatter/gather match the single-GPU framebuffers")
+        print(f"multi_gpu_check ok: world={world}, {total} samples, reduce + all-reduce + peer-memory combine + reduce-scatter/gather match the single-GPU framebuffers")
     dist.destroy_process_group()
 
 
