@@ -166,8 +166,8 @@ k_filter_classify(const __grid_constant__ FilterConsts fc, const __grid_constant
           }
         }
         if (pass && head) {
-          if (aovs.role[a] == 1 /*RGBA*/) atomicAdd(aovs.weight + pixel, w);
-          if (aovs.add_zeros || r.x != 0.0f || r.y != 0.0f || r.z != 0.0f || r.w != 0.0f) atomicAdd(aovs.buffer[a] + pixel, r);  // see add_to_buffer
+          if (aovs.role[a] == 1 /*RGBA*/) red_add(aovs.weight + pixel, w);
+          if (aovs.add_zeros || r.x != 0.0f || r.y != 0.0f || r.z != 0.0f || r.w != 0.0f) red_add(aovs.buffer[a] + pixel, r);  // see add_to_buffer
         }
       }
     }

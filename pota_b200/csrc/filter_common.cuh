@@ -5,6 +5,22 @@
 
 namespace lb {
 
+// Fire-and-forget reductions.  With LB_RED_PTX (the PO splat kernels, filter_kernels.cuh) they are spelled in PTX: there ptxas
+// otherwise emits `ATOMG ... RZ` -- an atomic whose result is thrown away but still travels back, counted by ncu as op_atom --
+// for the very atomicAdd calls it turns into REDG in the thin-lens and classify kernels.  Those keep the intrinsics: a volatile
+// asm statement pins the reduction in the instruction stream and the thin-lens splat measured 2.96 instead of 2.76 ms with it.
+#ifdef LB_RED_PTX
+LB_DEV void red_add(float4 *p, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
+}
+LB_DEV void red_add(float *p, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v)); }
+LB_DEV void red_min(unsigned long long *p, unsigned long long v) { asm volatile("red.global.min.u64 [%0], %1;" ::"l"(p), "l"(v)); }
+#else
+LB_DEV void red_add(float4 *p, float4 v) { atomicAdd(p, v); }
+LB_DEV void red_add(float *p, float v) { atomicAdd(p, v); }
+LB_DEV void red_min(unsigned long long *p, unsigned long long v) { atomicMin(p, v); }
+#endif
+
 // value of AOV `a` for sample i as filter_pixel gathers it (lentil_filter.cpp:206-234)
 LB_DEV float4 aov_value(const AovSet &aovs, const SampleIO &s, int a, size_t i, float debug_val) {
   if (aovs.filter[a] == 2 /*LB_FILTER_CRYPTO: no value, lentil_filter.cpp:208*/) return make_float4(0.f, 0.f, 0.f, 0.f);
@@ -28,7 +44,7 @@ LB_DEV unsigned long long closest_key(float depth, uint64_t sample_global) {
 LB_DEV void add_to_buffer(const AovSet &aovs, int a, unsigned pixel, float4 v, float add_energy, float depth,
                           float filter_weight, const float rgb_weight[3], uint64_t sample_global) {
   if (aovs.filter[a] == 0 /*gaussian*/) {
-    if (aovs.role[a] == 1 /*RGBA*/) atomicAdd(aovs.weight + pixel, filter_weight);
+    if (aovs.role[a] == 1 /*RGBA*/) red_add(aovs.weight + pixel, filter_weight);
     float4 r;
     r.x = (v.x + add_energy) * filter_weight * rgb_weight[0];
     r.y = (v.y + add_energy) * filter_weight * rgb_weight[1];
@@ -37,10 +53,10 @@ LB_DEV void add_to_buffer(const AovSet &aovs, int a, unsigned pixel, float4 v, f
     // An all-zero contribution is not sent: adding +-0 changes no bit of a buffer (it starts at +0 and round-to-nearest sums never
     // produce -0), and most AOVs of a production set are zero for most samples (a per-light AOV holds one light's samples) --
     // at 8K x 10 AOVs the planes are not L2-resident and every reduction is a DRAM read-modify-write.  NaNs compare unequal: sent.
-    if (aovs.add_zeros || r.x != 0.0f || r.y != 0.0f || r.z != 0.0f || r.w != 0.0f) atomicAdd(aovs.buffer[a] + pixel, r);
+    if (aovs.add_zeros || r.x != 0.0f || r.y != 0.0f || r.z != 0.0f || r.w != 0.0f) red_add(aovs.buffer[a] + pixel, r);
   } else {
-    if (aovs.role[a] != 2) atomicMin(aovs.zkey + pixel, closest_key(depth, sample_global));
-    else if (v.x != 0.0f) atomicMin(aovs.zkey_debug + pixel, closest_key(depth, sample_global));
+    if (aovs.role[a] != 2) red_min(aovs.zkey + pixel, closest_key(depth, sample_global));
+    else if (v.x != 0.0f) red_min(aovs.zkey_debug + pixel, closest_key(depth, sample_global));
   }
 }
 
@@ -57,7 +73,7 @@ LB_DEV void crypto_insert(uint32_t *__restrict__ keys, float *__restrict__ wgts,
     uint32_t cur = *(volatile uint32_t *)(k0 + h);
     if (cur == kCryptoFree) cur = atomicCAS(k0 + h, kCryptoFree, key);
     if (cur == kCryptoFree || cur == key) {
-      atomicAdd(w0 + h, w);
+      red_add(w0 + h, w);
       return;
     }
     h = h + 1 == (unsigned)slots ? 0u : h + 1;
@@ -70,7 +86,7 @@ LB_DEV void crypto_insert(uint32_t *__restrict__ keys, float *__restrict__ wgts,
 LB_DEV void crypto_add(const AovSet &aovs, int a, size_t i, bool on, unsigned pixel, float sample_weight, FilterCounters *counters) {
   const int stride = aovs.crypto_depth > 1 ? aovs.crypto_depth : 1;
   const float2 *e = aovs.crypto_cache[a] + i * (size_t)stride;
-  if (on && a == aovs.crypto_first) atomicAdd(&aovs.buffer[a][pixel].x, sample_weight);  // crypto_total_weight, one plane for every cryptomatte AOV
+  if (on && a == aovs.crypto_first) red_add(&aovs.buffer[a][pixel].x, sample_weight);  // crypto_total_weight, one plane for every cryptomatte AOV
   for (int j = 0; j < stride; ++j) {
     const float2 kv = e[j];
     if (__float_as_uint(kv.x) == kCryptoFree) break;

@@ -19,6 +19,7 @@
 // per attempt (mean ~30, up to 100), and a per-attempt inner loop left 2/3 of the lanes idle
 // (profiles/r01_k2_filter_splat_ncu.txt: 10.97 of 32 lanes active).
 #pragma once
+#define LB_RED_PTX 1  // the PO splat kernels issue their reductions as PTX `red` (see filter_common.cuh)
 #include "filter_common.cuh"
 
 namespace lb {

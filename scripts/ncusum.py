@@ -26,7 +26,15 @@ want = ["Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "lau
         "lts__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__sass_thread_inst_executed_op_ffma_pred_on.sum",
         "smsp__sass_thread_inst_executed_op_fmul_pred_on.sum", "smsp__sass_thread_inst_executed_op_fadd_pred_on.sum", "sm__cycles_elapsed.max",
         "smsp__warps_eligible.avg.per_cycle_active", "sm__sass_thread_inst_executed_op_ffma_pred_on.sum", "sm__sass_thread_inst_executed_op_fmul_pred_on.sum",
-        "sm__sass_thread_inst_executed_op_fadd_pred_on.sum"]
+        "sm__sass_thread_inst_executed_op_fadd_pred_on.sum",
+        # the splat accumulate: reductions as the L2 slices see them (sectors, share of the slices' peak, hit / miss), and on the way there
+        "lts__t_sectors_srcunit_tex_op_red.sum", "lts__t_sectors_srcunit_tex_op_red.sum.pct_of_peak_sustained_elapsed",
+        "lts__t_sectors_srcunit_tex_op_red.sum.per_second", "lts__t_sectors_srcunit_tex_op_red_lookup_hit.sum",
+        "lts__t_sectors_srcunit_tex_op_red_lookup_miss.sum", "lts__t_sectors_srcunit_tex_op_atom.sum", "lts__t_requests_srcunit_tex_op_red.sum",
+        "l1tex__m_l1tex2xbar_write_sectors_mem_global_op_red.sum", "l1tex__m_l1tex2xbar_write_sectors_mem_global_op_red.sum.pct_of_peak_sustained_elapsed",
+        "l1tex__t_requests_pipe_lsu_mem_global_op_red.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_atom.sum",
+        "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
+        "lts__t_sectors.sum.pct_of_peak_sustained_elapsed"]
 for i, h in enumerate(hdr):
     if h in want or (h.startswith("smsp__average_warps_issue_stalled") and h.endswith("_per_issue_active.ratio")) or \
             (h.startswith("smsp__average_warp_latency_issue_stalled") and h.endswith(".ratio")):

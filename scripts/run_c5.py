@@ -25,7 +25,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--spp", type=int, default=16)
     ap.add_argument("--steps", type=int, default=2)
-    ap.add_argument("--combine", default="peer", choices=["peer", "scatter", "reduce"])
+    ap.add_argument("--combine", default="peer", choices=["peer", "scatter", "reduce", "both"], help="both: the peer combine, then reduce-scatter + gather, on the same partials of every step")
     ap.add_argument("--tile", type=int, default=4)
     ap.add_argument("--emulate-world", type=int, default=0, help="single GPU: accumulate rank 0's share of an N-rank run (no combine partner)")
     ap.add_argument("--order", default="row", choices=["row", "bucket"], help="sample order of a batch: row-major, or 128x128 render buckets")
@@ -62,6 +62,7 @@ def main():
     chunk = 1920 * 1080 * 16  # source samples generated and accumulated per call
     stream = torch.cuda.current_stream()
     times = []
+    peer_sum, scatter_sum = [], []
     for step in range(a.steps + 1):
         cam.filter_begin(W, H, aovs)
         cam.filter_set_sample_base(base)
@@ -80,15 +81,32 @@ def main():
         e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         if world > 1:
             dist.barrier()
+        t_peer = 0.0
+        if a.combine == "both":  # the peer combine leaves the partial planes as they are: the NCCL path below runs on the same frame
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            p0.record(stream)
+            imgs = cam.resolve_peer(range(len(aovs)), root=0, stream=stream)
+            p1.record(stream)
+            torch.cuda.synchronize()
+            t_peer = p0.elapsed_time(p1)
+            if rank == 0 and step == a.steps:
+                peer_sum = [float(i[..., :3].double().sum()) for i in imgs]
+            del imgs
+            if world > 1:
+                dist.barrier()
         e0.record(stream)
         if a.combine == "peer":  # one kernel: sum over NVLink peer memory + resolve + store on rank 0, all AOVs
             e1.record(stream)
             imgs = cam.resolve_peer(range(len(aovs)), root=0, stream=stream)
-        elif a.combine == "scatter":
+        elif a.combine in ("scatter", "both"):
             cam.filter_reduce_scatter(stream=stream)
             e1.record(stream)
             out = torch.empty((H, W, 4), dtype=torch.float32, device=dev) if rank == 0 else None
-            imgs = [cam.resolve_gather(k, root=0, stream=stream, out=out) for k in range(len(aovs))]  # one reusable 531 MB image
+            imgs = []
+            for k in range(len(aovs)):  # one reusable 531 MB image
+                imgs.append(cam.resolve_gather(k, root=0, stream=stream, out=out))
+                if a.combine == "both" and rank == 0 and step == a.steps:
+                    scatter_sum.append(float(out[..., :3].double().sum()))
         else:
             cam.filter_reduce(root=0, stream=stream)
             e1.record(stream)
@@ -98,9 +116,9 @@ def main():
         t_red, t_res = e0.elapsed_time(e1), e1.elapsed_time(e2)
         st = cam.filter_stats()
         if step > 0:
-            times.append((t_acc, t_red, t_res, st["splats"]))
+            times.append((t_acc, t_red, t_res, st["splats"], t_peer))
         del imgs
-    t = torch.tensor([[x[0], x[1], x[2], x[3]] for x in times], dtype=torch.float64, device=dev).mean(0)
+    t = torch.tensor([[x[0], x[1], x[2], x[3], x[4]] for x in times], dtype=torch.float64, device=dev).mean(0)
     tmax = t.clone()
     tsum = t.clone()
     if world > 1:
@@ -113,7 +131,9 @@ def main():
         print("C5 " + json.dumps({"tag": a.tag, "order": a.order, "camera": "thinlens" if a.thin else "po", "emulate_world": a.emulate_world, "config": f"C5 {W}x{H}x{a.spp}spp, {len(aovs)} AOVs (9 gaussian RGBA + 1 closest), {world} GPU(s)", "combine": a.combine,
                           "partition": f"hashed {a.tile}x{a.tile} pixel tiles", "accumulate_ms": float(tmax[0]),
                           "reduce_ms": float(tmax[1]), "resolve_gather_ms": float(tmax[2]), "splats": splats, "splats_per_s": splats / (total_ms * 1e-3),
-                          "framebuffer_block_GB": block_gb, "reduce_GBps_per_rank": block_gb / (float(tmax[1]) * 1e-3) if world > 1 else None}))
+                          "framebuffer_block_GB": block_gb, "reduce_GBps_per_rank": block_gb / (float(tmax[1]) * 1e-3) if world > 1 and float(tmax[1]) > 0 else None,
+                          "peer_combine_resolve_gather_ms": float(tmax[4]) if a.combine == "both" else None,
+                          "peer_vs_scatter_image_sums_rel_diff": (max(abs(x - y) / max(abs(y), 1e-30) for x, y in zip(peer_sum, scatter_sum)) if peer_sum and scatter_sum else None)}))
     if world > 1:
         dist.destroy_process_group()
 
