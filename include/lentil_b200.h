@@ -330,7 +330,9 @@ LB_API int lb_imager_resolve_gather(lb_camera *cam, int aov, float *rgba_out, in
  * lb_filter_begin -- the mappings are renewed when buffers are reallocated).  aov_indices: n_out AOVs (no cryptomatte AOVs).
  * images_out: NULL, or n_out device pointers ([yres][xres][4] floats; entries may be NULL) the receiving ranks copy the
  * images to; without it they are read in place through lb_imager_peer_image.  The partial planes are left untouched.
- * At most 8 ranks, world size dividing 5040; single rank / no communicator: a plain resolve of every listed AOV. */
+ * Slabs: even over the ranks; when one rank receives (root >= 0) and there are three or more ranks, the receiver owns no slab
+ * (its NVLink ingress is the limit: it takes in the images only).  At most 8 ranks; single rank / no communicator: a plain
+ * resolve of every listed AOV. */
 LB_API int lb_imager_resolve_peer(lb_camera *cam, int n_out, const int *aov_indices, float *const *images_out, int root,
                                   lb_stream stream);
 /* Device pointer to the [yres][xres][4] image of `aov` that the last lb_imager_resolve_peer left on this (receiving) rank;

@@ -1038,7 +1038,6 @@ int lb_imager_resolve_peer(lb_camera *c, int n_out, const int *aov_indices, floa
     if (f->crypto_of[aov_indices[k]] >= 0) return lb_fail(LB_ERR_INVALID, "cryptomatte AOVs combine with lb_filter_reduce (id tables are merged, not summed)");
   }
   if (f->world > FilterState::kMaxPeers) return lb_fail(LB_ERR_INVALID, "more than 8 ranks: use lb_filter_reduce_scatter");
-  if (f->npx_pad % (size_t)f->world) return lb_fail(LB_ERR_INVALID, "world size does not divide the plane granule (5040): use lb_filter_reduce");
   if (f->scattered) return lb_fail(LB_ERR_STATE, "lb_filter_reduce_scatter has already consumed this frame's partial planes");
   std::lock_guard<std::mutex> lk(cam_mutex(c));
   DeviceGuard g(cam_device(c));
@@ -1077,9 +1076,15 @@ int lb_imager_resolve_peer(lb_camera *c, int n_out, const int *aov_indices, floa
   }
   // barrier: every rank's accumulates have finished (and nobody still reads the previous frame's images) before any rank loads
   if (!single && (rc = check(n->AllReduce(f->barrier_word, f->barrier_word + 1, 1, ncclFloat32, ncclSum, f->comm, stream))) != LB_OK) return rc;
-  const size_t slab = f->npx_pad / (size_t)P.world;
-  const size_t lo = single ? 0 : (size_t)f->rank * slab;
-  const size_t cnt = lo < f->npx ? std::min(slab, f->npx - lo) : 0;
+  // Who owns which pixels.  Every owner pulls its slab from all other ranks, and the receiving rank also takes in every owner's
+  // resolved pixels -- with even slabs its NVLink ingress is (N-1)/N of (planes + images) against (N-1)/N of the planes for
+  // the others (config C5, N = 8: 9.4 GB vs 4.8 GB, and the step waits for it).  So when one rank receives the image and
+  // there are three or more ranks, that rank owns no slab: it only receives (5.3 GB), the others pull slabs of 1/(N-1).
+  const int owners = (!single && root >= 0 && P.world >= 3) ? P.world - 1 : P.world;
+  const int owner_idx = owners == P.world ? f->rank : (f->rank == root ? -1 : (f->rank < root ? f->rank : f->rank - 1));
+  const size_t slab = ((f->npx + (size_t)owners - 1) / (size_t)owners + 255) / 256 * 256;
+  const size_t lo = single || owner_idx < 0 ? 0 : (size_t)owner_idx * slab;
+  const size_t cnt = owner_idx < 0 ? 0 : (lo < f->npx ? std::min(slab, f->npx - lo) : 0);
   if (cnt) {
     const unsigned grid = (unsigned)std::min<size_t>((cnt + 255) / 256, (size_t)cam_num_sms(c) * 16);
     k_resolve_peer<<<grid, 256, 0, stream>>>(P, lo, cnt);
