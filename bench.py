@@ -618,6 +618,15 @@ def bench_splat(args, rank, world, local_rank, dev, barrier, max_over_ranks, sum
         return cam.resolve_gather(0, root=0, stream=stream, out=out_img)
 
     steps = max(1, min(args.steps, 5))
+    if world > 1 and combine == "peer":
+        try:  # the failure is collective (every rank gets the error), so every rank falls back together
+            step()
+        except Exception as e:  # noqa: BLE001
+            if rank == 0:
+                print(f"bench.py: peer-memory combine unavailable ({e}); using reduce-scatter + gather", file=sys.stderr)
+            combine = "scatter"
+            partition = partition.replace("combine + resolve + gather on rank 0 in one kernel over NVLink peer memory (lb_imager_resolve_peer)",
+                                          "ncclReduceScatter per plane, per-rank resolve, gather on rank 0")
     for _ in range(2):
         step()
     barrier()

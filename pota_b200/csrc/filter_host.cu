@@ -1006,6 +1006,7 @@ int peer_exchange(FilterState *f, NcclApi *n, cudaStream_t stream) {
   std::vector<unsigned char> all((size_t)f->world * kIpcBytes);
   CUF(cudaMemcpyAsync(all.data(), f->ipc_dev, all.size(), cudaMemcpyDeviceToHost, stream));
   CUF(cudaStreamSynchronize(stream));
+  bool opened = true;
   for (int r = 0; r < f->world; ++r) {
     if (r == f->rank) {
       f->peer_block[r] = f->block; f->peer_zkey[r] = f->zkey; f->peer_zkey_debug[r] = f->zkey_debug; f->peer_img[r] = f->img_block;
@@ -1015,13 +1016,23 @@ int peer_exchange(FilterState *f, NcclApi *n, cudaStream_t stream) {
     for (int k = 0; k < 4; ++k) {
       cudaIpcMemHandle_t h;
       memcpy(&h, all.data() + (size_t)r * kIpcBytes + k * sizeof h, sizeof h);
-      const cudaError_t e = cudaIpcOpenMemHandle(&ptr[k], h, cudaIpcMemLazyEnablePeerAccess);
-      if (e != cudaSuccess) return lb_fail(LB_ERR_COMM, "cudaIpcOpenMemHandle failed (no peer access between the ranks' devices?): use lb_filter_reduce_scatter");
+      if (cudaIpcOpenMemHandle(&ptr[k], h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ptr[k] = nullptr; opened = false; cudaGetLastError(); }
     }
     f->peer_block[r] = (float *)ptr[0]; f->peer_zkey[r] = (unsigned long long *)ptr[1];
     f->peer_zkey_debug[r] = (unsigned long long *)ptr[2]; f->peer_img[r] = (float4 *)ptr[3];
   }
-  f->peer_gen = f->alloc_gen;
+  // the outcome is collective: a rank that could not map a peer must not leave the others waiting in the barrier below
+  float flag[2] = {opened ? 0.0f : 1.0f, 0.0f};
+  CUF(cudaMemcpyAsync(f->barrier_word, flag, 4, cudaMemcpyHostToDevice, stream));
+  if ((rc = check(n->AllReduce(f->barrier_word, f->barrier_word + 1, 1, ncclFloat32, ncclSum, f->comm, stream))) != LB_OK) return rc;
+  CUF(cudaMemcpyAsync(flag + 1, f->barrier_word + 1, 4, cudaMemcpyDeviceToHost, stream));
+  CUF(cudaMemsetAsync(f->barrier_word, 0, 4, stream));
+  CUF(cudaStreamSynchronize(stream));
+  f->peer_gen = f->alloc_gen;  // (mappings exist: peer_release below / later closes them)
+  if (flag[1] != 0.0f) {
+    peer_release(f);
+    return lb_fail(LB_ERR_COMM, "cudaIpcOpenMemHandle failed on some rank (no peer access between the devices?): use lb_filter_reduce_scatter");
+  }
   return LB_OK;
 }
 }  // namespace
