@@ -268,7 +268,7 @@ LB_API int lb_filter_begin(lb_camera *cam, const lb_frame_desc *frame, int n_aov
  * the planes): each waits on the device for the previous accumulate / reduce / resolve of that camera. */
 LB_API int lb_filter_accumulate(lb_camera *cam, const lb_samples *samples, lb_stream stream);
 /* Same with every pointer in lb_samples (and aov_values[i]) a HOST pointer (pinned or pageable): the samples travel in
- * chunks through two device staging blocks, the copy of one chunk beside the kernels of the previous one. */
+ * chunks through a ring of six device staging blocks, the copies running ahead of the kernels of the previous chunks. */
 LB_API int lb_filter_accumulate_host(lb_camera *cam, const lb_samples *samples);
 LB_API int lb_filter_get_stats(lb_camera *cam, lb_filter_stats *out); /* synchronises */
 /* Diagnostic: lt_sample_aperture Newton iterations executed since lb_filter_begin (synchronises). */

@@ -65,7 +65,7 @@ struct FilterState {
     cudaStream_t last_stream = nullptr;
     bool used = false;
   };
-  static constexpr int kScratch = 4;
+  static constexpr int kScratch = 6;
   Scratch scratch[kScratch];
   int next_scratch = 0;
   cudaEvent_t ev_accum = nullptr;     // scratch for "wait for every accumulate in flight"
@@ -79,11 +79,15 @@ struct FilterState {
   uint64_t sample_base = 0;
   uint64_t samples_seen = 0;  // source samples handed to accumulate since lb_filter_begin
   // host-path staging: two device blocks so that the copy of chunk k+1 overlaps the kernels of chunk k
-  char *stage[3] = {nullptr, nullptr, nullptr};
+  // kStage blocks in flight: a chunk's block is held until its splat kernel has finished (the kernel reads the AOV values from
+  // it), and chunks that hold highlights run for milliseconds -- with three blocks the copies stalled behind them
+  static constexpr int kStage = 6;  // at most (12 measured no faster); a call uses as many as fit 2 GiB (>= 3)
+  char *stage[kStage] = {};
   size_t stage_bytes = 0;
-  cudaEvent_t stage_ready[3] = {nullptr, nullptr, nullptr}, stage_free[3] = {nullptr, nullptr, nullptr};
+  int stage_slots = 0;  // blocks allocated
+  cudaEvent_t stage_ready[kStage] = {}, stage_free[kStage] = {};
   cudaStream_t stream = nullptr, copy_stream = nullptr;
-  cudaStream_t work_stream[3] = {nullptr, nullptr, nullptr};  // lb_filter_accumulate_host: chunk k runs on work_stream[k % 3]
+  cudaStream_t work_stream[kStage] = {};  // lb_filter_accumulate_host: chunk k runs on work_stream[k % kStage]
   // lb_imager_resolve_host: the whole region of an AOV is resolved once into pinned host memory, buckets are served from it
   float4 *res_dev = nullptr;           // [npx]
   uint8_t *brk_dev = nullptr;          // [npx] cryptomatte: pixel holds <= rank ids (ends a bucket row, lentil_imager.cpp:132-134)
@@ -362,7 +366,7 @@ void filter_state_destroy(FilterState *f) {
   cudaFree(f->crypto_tables);
   cudaFree(f->d_counters); cudaFree(f->gather); cudaFree(f->res_dev); cudaFree(f->brk_dev);
   for (int a = 0; a < kMaxAov; ++a) { cudaFreeHost(f->res_host[a]); cudaFreeHost(f->brk_host[a]); }
-  for (int i = 0; i < 3; ++i) {
+  for (int i = 0; i < FilterState::kStage; ++i) {
     cudaFree(f->stage[i]);
     if (f->stage_ready[i]) cudaEventDestroy(f->stage_ready[i]);
     if (f->stage_free[i]) cudaEventDestroy(f->stage_free[i]);
@@ -506,7 +510,7 @@ int lb_filter_accumulate_host(lb_camera *c, const lb_samples *S) {
   if (S->n == 0) return LB_OK;
   std::lock_guard<std::mutex> lk(cam_mutex(c));
   DeviceGuard g(cam_device(c));
-  constexpr int kSlots = 3;
+  constexpr int kSlots = FilterState::kStage;
   const size_t chunk = std::min<size_t>(S->n, (size_t)1 << 21);
   int n_val = 0;
   for (int a = 0; a < f->n_aov; ++a) if (S->aov_values && S->aov_values[a]) ++n_val;
@@ -517,7 +521,8 @@ int lb_filter_accumulate_host(lb_camera *c, const lb_samples *S) {
   const size_t per = 8 + 32 + (S->raydir ? 16 : 0) + (S->transmission ? 16 : 0) + (S->flags ? 4 : 0) + 16 * (size_t)n_val +
                      (Dn ? 1 + 4 * Dn * (1 + (size_t)n_ids) : 0);
   const size_t need = per * chunk + 256 * (16 + 2 * kMaxAov);
-  if (f->stage_bytes < need) {
+  const int n_slots = (int)std::min<size_t>((size_t)kSlots, std::max<size_t>(3, ((size_t)2 << 30) / need));
+  if (f->stage_bytes < need || f->stage_slots < n_slots) {
     for (int i = 0; i < kSlots; ++i) {
       cudaFree(f->stage[i]); f->stage[i] = nullptr;
       if (!f->stage_ready[i]) CUF(cudaEventCreateWithFlags(&f->stage_ready[i], cudaEventDisableTiming));
@@ -525,15 +530,17 @@ int lb_filter_accumulate_host(lb_camera *c, const lb_samples *S) {
       if (!f->work_stream[i]) CUF(cudaStreamCreateWithFlags(&f->work_stream[i], cudaStreamNonBlocking));
     }
     f->stage_bytes = 0;
-    for (int i = 0; i < kSlots; ++i) CUF(cudaMalloc(&f->stage[i], need));
+    f->stage_slots = 0;
+    for (int i = 0; i < n_slots; ++i) CUF(cudaMalloc(&f->stage[i], need));
     f->stage_bytes = need;
+    f->stage_slots = n_slots;
   }
   int rc = LB_OK;
   size_t k = 0;
   for (size_t base = 0; base < S->n && rc == LB_OK; base += chunk, ++k) {
-    const int slot = (int)(k % kSlots);
+    const int slot = (int)(k % n_slots);
     const size_t m = std::min(chunk, S->n - base);
-    if (k >= (size_t)kSlots) CUF(cudaStreamWaitEvent(f->copy_stream, f->stage_free[slot], 0));  // the kernels of chunk k-3 have read this block
+    if (k >= (size_t)n_slots) CUF(cudaStreamWaitEvent(f->copy_stream, f->stage_free[slot], 0));  // the kernels of chunk k - kStage have read this block
     char *p = f->stage[slot];
     auto put = [&](const void *src, size_t elem) -> void * {
       if (!src) return nullptr;
