@@ -62,7 +62,7 @@ static int run(int camera_type, int lens_model, bool with_bokeh) {
   size_t live = 0;
   for (size_t i = 0; i < n; ++i) live += out[6][i] != 0.f;
   // ---- redistribution: RGBA + a light AOV + closest + lentil_debug + two ranked cryptomatte AOVs ----
-  const int W = 96, H = 54, spp = 4, D = 3;
+  const int W = 128, H = 72, spp = 4, D = 3;  // >= 64 in both directions: LB_SPLAT_TILE=1 runs the shared-memory tile kernel
   lb_aov_desc aovs[6];
   memset(aovs, 0, sizeof aovs);
   const char *names[6] = {"RGBA", "light0", "N", "lentil_debug", "crypto_material00", "crypto_object01"};
