@@ -14,8 +14,10 @@ GENROOT := $(OUT)/gen
 # leading ../ components are absorbed by dummy path segments
 INC := -I$(HERE)shims -I$(HERE)shims/a/b -I$(HERE)shims/a -I$(GENROOT)/a/b/c -I$(REF)/src
 CXXFLAGS ?= -std=c++17 -O3 -DNDEBUG -fPIC -ffp-contract=off -pthread -w
-SRCS := $(REF)/src/lentil.cpp $(REF)/src/lentil_camera.cpp $(REF)/src/lentil_filter.cpp $(REF)/src/lentil_imager.cpp
-OBJS := $(OUT)/lentil.o $(OUT)/lentil_camera.o $(OUT)/lentil_filter.o $(OUT)/lentil_imager.o $(OUT)/ref_harness.o
+SRCS := $(REF)/src/lentil.cpp $(REF)/src/lentil_camera.cpp $(REF)/src/lentil_filter.cpp $(REF)/src/lentil_imager.cpp \
+        $(REF)/src/lentil_operator.cpp $(REF)/src/lentil_loader.cpp
+OBJS := $(OUT)/lentil.o $(OUT)/lentil_camera.o $(OUT)/lentil_filter.o $(OUT)/lentil_imager.o $(OUT)/lentil_operator.o $(OUT)/lentil_loader.o \
+        $(OUT)/ref_harness.o
 PACK := $(wildcard $(HERE)../pota_b200/lenses/*.json)
 
 all: $(OUT)/libref.so

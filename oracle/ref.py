@@ -41,7 +41,27 @@ def _declare_scenario_api(L):
     L.ref_imager_resolve.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]
     L.ref_filter_buffers.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(vp)]
     L.ref_filter_crypto.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp]
+    L.ref_camera_use_operator.argtypes = [vp, C.c_int]
+    L.ref_node_loader.argtypes = [C.c_char_p, C.c_size_t]
+    L.ref_operator_cook.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_size_t]
     return L
+
+
+def node_loader(L) -> list[str]:
+    """what NodeLoader(i, ...) answers for i = 0, 1, ... (lentil_loader.cpp:20-28), one line per node"""
+    buf = C.create_string_buffer(1 << 14)
+    L.ref_node_loader(buf, len(buf))
+    return buf.value.decode().splitlines()
+
+
+def operator_cook(L, scene: str, cooks: int = 1) -> list[str]:
+    """operator_init + operator_cook of the library's lentil_operator node on the scene (see ref_operator_cook in
+    oracle/ref_harness.cpp for the scene lines) -> everything the cook leaves behind, as text lines"""
+    buf = C.create_string_buffer(1 << 18)
+    rc = L.ref_operator_cook(scene.encode(), cooks, buf, len(buf))
+    if rc != 0:
+        raise RuntimeError(f"ref_operator_cook: {rc}")
+    return buf.value.decode().splitlines()
 
 
 ADAPTOR_LIB_PATH = os.path.join(os.path.dirname(HERE), "adaptor", "_build", "libadaptor.so")
@@ -96,6 +116,7 @@ def lib():
         L.ref_lens_lt_sample_aperture.argtypes = [vp, vp, vp, vp, vp, C.c_double]
         L.ref_trace_ray_bw_po.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_float, vp]
         L.ref_bokeh_sample.argtypes = [vp, C.c_float, C.c_float, vp]
+        _declare_scenario_api(L)
         _LIB = L
     return _LIB
 
@@ -143,6 +164,11 @@ class RefCamera(orc.OracleCamera):
 
     def counters(self):
         raise NotImplementedError("the reference keeps no counters")
+
+    def use_operator(self, on: bool = True):
+        """from the next filter_begin on, the AOV list is what the library's own lentil_operator node cooks from the scene's
+        outputs (lentil_operator.cpp:25-171): the given AOVs, then lentil_debug, lentil_time, lentil_raydir as AOVs n, n+1, n+2"""
+        self._L().ref_camera_use_operator(self._h, int(on))
 
     def filter_begin(self, xres, yres, aovs, xres_full=None, yres_full=None, region_min=(0, 0), spp=9):
         aa = int(round(math.sqrt(spp)))

@@ -11,6 +11,7 @@
 #include <ai.h>
 
 #include <chrono>
+#include <deque>
 #include <iostream>
 #include <regex>
 #include <thread>
@@ -35,10 +36,14 @@ typedef LbAdaptorCamera Camera;
 extern const AtNodeMethods *lentilMethods;         // lentil_camera.cpp:5
 extern const AtNodeMethods *LentilFilterDataMtd;   // lentil_filter.cpp:6
 extern const AtNodeMethods *LentilImagerMtd;       // lentil_imager.cpp:7
+extern const AtNodeMethods *LentilOperatorMtd;     // lentil_operator.cpp:8
+extern "C" bool NodeLoader(int i, AtNodeLib *node);  // lentil_loader.cpp:20-28
 
 struct ref_camera {
   AtUniverse uni;
-  AtNode options, camera, filter, imager, op, crypto, exr;
+  AtNode options, camera, filter, imager, op, crypto, exr, f_gauss, f_closest, f_crypto;
+  bool use_operator = false;  // the AOV list comes from the library's own lentil_operator node instead of build_operator_aovs
+  void *op_user = nullptr;
   CryptomatteData cryptodata;
   AtArray aov_shaders, outputs;
   OperatorData opdata;
@@ -46,6 +51,8 @@ struct ref_camera {
   std::vector<lb_aov_desc> aovs;
   lb_frame_desc frame{};
   int aa = 3;
+  size_t scene_nodes = 0;  // uni.nodes entries that belong to the scene itself
+  size_t n_user_aovs = 0;  // aovs[0 .. n_user_aovs) came with ref_filter_begin, the rest are the operator's helper outputs
 #ifdef LB_ADAPTOR
   std::vector<float> host_buffer, host_weight;  // lb_filter_buffers_host copies handed out by ref_filter_buffers
 #endif
@@ -119,16 +126,27 @@ void update_camera(ref_camera *r) {
   set_b(o, "ignore_dof", false);
   set_b(o, "enable_progressive_render", false);
   set_f(o, "meters_per_unit", 0.01f);
-  build_operator_aovs(r);
+  if (!r->use_operator) build_operator_aovs(r);
   // cryptomatte: a `cryptomatte` AOV shader whose setup has completed (lentil.h:244-270) and ranked crypto outputs
   // written by an EXR driver (lentil.h:1104-1114)
   r->aov_shaders.ptrs.clear();
   r->outputs.strs.clear();
-  for (auto &a : r->aovs)
-    if (a.filter == LB_FILTER_CRYPTO) r->outputs.strs.push_back(std::string(a.name) + " FLOAT cryptomatte_filter shim_exr");
-  if (!r->outputs.strs.empty()) r->aov_shaders.ptrs.push_back(&r->crypto);
+  bool any_crypto = false;
+  for (auto &a : r->aovs) {
+    if (a.filter == LB_FILTER_CRYPTO) { r->outputs.strs.push_back(std::string(a.name) + " FLOAT cryptomatte_filter shim_exr"); any_crypto = true; }
+    else if (r->use_operator)  // the scene as exported: every output still on its original filter node
+      r->outputs.strs.push_back(std::string(a.name) + " RGBA " + (a.filter == LB_FILTER_CLOSEST ? "shim_closest" : "shim_gaussian") + " shim_driver");
+  }
+  if (any_crypto) r->aov_shaders.ptrs.push_back(&r->crypto);
   AiNodeSetArray(&o, AtString("aov_shaders"), &r->aov_shaders);
   AiNodeSetArray(&o, AtString("outputs"), &r->outputs);
+  if (r->use_operator) {  // operator_init + operator_cook of the node table NodeLoader hands out, on a fresh OperatorData per update
+    if (r->op.local_data != &r->opdata) LentilOperatorMtd->OperatorCleanup(&r->op, r->op_user);
+    while (r->uni.nodes.size() > r->scene_nodes) r->uni.nodes.pop_back();  // nodes made by the previous cook
+    r->uni.created.clear();
+    LentilOperatorMtd->OperatorInit(&r->op, &r->op_user);
+    LentilOperatorMtd->OperatorCook(&r->op, &r->op, r->op_user, nullptr, nullptr);
+  }
   lentilMethods->Update(&r->uni.session, &r->camera);
   r->cam = (Camera *)AiNodeGetLocalData(&r->camera);
 }
@@ -140,7 +158,11 @@ int ref_camera_create(const lb_camera_params *p, const lb_bokeh_image *img, ref_
   ref_camera *r = new ref_camera();
   r->uni.options = &r->options;
   r->uni.camera = &r->camera;
-  r->uni.nodes = {&r->options, &r->camera, &r->filter, &r->imager, &r->op, &r->crypto, &r->exr};
+  r->uni.nodes = {&r->options, &r->camera, &r->filter, &r->imager, &r->op, &r->crypto, &r->exr, &r->f_gauss, &r->f_closest, &r->f_crypto};
+  r->scene_nodes = r->uni.nodes.size();
+  r->f_gauss.name = "shim_gaussian"; r->f_gauss.entry.name = "gaussian_filter";
+  r->f_closest.name = "shim_closest"; r->f_closest.entry.name = "closest_filter";
+  r->f_crypto.name = "cryptomatte_filter"; r->f_crypto.entry.name = "cryptomatte_filter";
   r->crypto.name = "cryptomatte_shader"; r->crypto.entry.name = "cryptomatte"; r->crypto.local_data = &r->cryptodata;
   r->exr.name = "shim_exr"; r->exr.entry.name = "driver_exr";
   r->uni.entry_counts["imager_denoiser_oidn"] = 1;  // -> filter_width 1.0 (lentil.h:1083-1088): no footprint overlap
@@ -175,7 +197,19 @@ void ref_camera_destroy(ref_camera *r) {
   if (!r) return;
   shim_default_universe() = &r->uni;
   lentilMethods->Finish(&r->camera);
+  if (r->op.local_data != &r->opdata) LentilOperatorMtd->OperatorCleanup(&r->op, r->op_user);
   delete r;
+}
+// From the next ref_filter_begin on, the camera's AOV list is what the library's own lentil_operator node cooks from the scene's
+// outputs (every AOV on its original gaussian / closest filter node): the user's AOVs followed by lentil_debug, lentil_time and
+// lentil_raydir (lentil_operator.cpp:103-128).  Off: the harness writes the list itself (build_operator_aovs).
+int ref_camera_use_operator(ref_camera *r, int on) {
+  if (!on && r->op.local_data != &r->opdata) {
+    LentilOperatorMtd->OperatorCleanup(&r->op, r->op_user);
+    r->op.local_data = &r->opdata;
+  }
+  r->use_operator = on != 0;
+  return LB_OK;
 }
 
 int ref_camera_get_state(const ref_camera *r, lb_camera_state *s) {
@@ -253,7 +287,18 @@ int ref_filter_begin(ref_camera *r, const lb_frame_desc *f, int n_aov, const lb_
   r->frame = *f;
   r->aovs.assign(aovs, aovs + n_aov);
   r->aa = aa_samples;
+  r->n_user_aovs = r->aovs.size();
   update_camera(r);  // node_update -> setup_camera -> setup_lentil_aovs/setup_filter (lentil.h:211-281)
+  if (r->use_operator) {  // the operator's helper outputs become AOVs n, n+1, n+2 of ref_imager_resolve / ref_filter_buffers
+    const struct { const char *name; int filter, role; } extra[3] = {{"lentil_debug", LB_FILTER_CLOSEST, LB_AOV_LENTIL_DEBUG},
+                                                                     {"lentil_time", LB_FILTER_GAUSSIAN, LB_AOV_PLAIN},
+                                                                     {"lentil_raydir", LB_FILTER_GAUSSIAN, LB_AOV_PLAIN}};
+    for (auto &e : extra) {
+      lb_aov_desc d{};
+      strcpy(d.name, e.name); d.filter = e.filter; d.role = e.role;
+      r->aovs.push_back(d);
+    }
+  }
   return r->cam->redistribution ? LB_OK : LB_ERR_STATE;
 }
 
@@ -284,7 +329,7 @@ int ref_filter_accumulate(ref_camera *r, const lb_samples *S, int nthreads) {
   it.aovs["lentil_time"] = {zero.data(), 1};
   it.aovs["lentil_raydir"] = {S->raydir ? S->raydir : zero.data(), 3};
   it.aovs["transmission"] = {S->transmission ? S->transmission : zero.data(), 4};
-  for (size_t a = 0; a < r->aovs.size(); ++a) {
+  for (size_t a = 0; a < r->n_user_aovs; ++a) {
     if (r->aovs[a].filter == LB_FILTER_CRYPTO) {
       it.depth_ids[r->aovs[a].name] = (S->crypto_ids && S->crypto_ids[a]) ? S->crypto_ids[a] : nullptr;
       continue;
@@ -333,6 +378,132 @@ int ref_imager_resolve(ref_camera *r, int aov, int x0, int y0, int w, int h, flo
   oit.outs.push_back({AtString(r->aovs[aov].name), AI_TYPE_RGBA, rgba_out});
   LentilImagerMtd->DriverProcessBucket(&r->imager, &oit, nullptr, x0, y0, w, h, 0);
   return LB_OK;
+}
+
+// ---- the operator (lentil_operator.cpp:19-191) and the plugin entry point (lentil_loader.cpp:20-28) -----------------------
+// NodeLoader's answers for i = 0, 1, ... as text: `<i> <name> type=<node_type> out=<output_type> version=<v> methods=<which table>`
+int ref_node_loader(char *dump, size_t cap) {
+  std::string out;
+  int i = 0;
+  for (;; ++i) {
+    AtNodeLib lib;
+    memset(&lib, 0, sizeof lib);
+    if (!NodeLoader(i, &lib)) break;
+    const char *table = lib.methods == lentilMethods ? "camera" : lib.methods == LentilFilterDataMtd ? "filter"
+                      : lib.methods == LentilImagerMtd ? "imager" : lib.methods == LentilOperatorMtd ? "operator" : "?";
+    out += std::to_string(i) + " " + (lib.name ? lib.name : "") + " type=" + std::to_string(lib.node_type) + " out=" + std::to_string((int)lib.output_type) +
+           " version=" + lib.version + " methods=" + table + "\n";
+    if (i > 64) break;
+  }
+  if (dump && cap) { strncpy(dump, out.c_str(), cap - 1); dump[cap - 1] = 0; }
+  return i;
+}
+
+namespace {
+struct ShimScene {  // a universe described line by line (ref_operator_cook)
+  AtUniverse uni;
+  std::deque<AtNode> nodes;
+  AtNode *options = nullptr, *camera = nullptr, *op = nullptr;
+  AtArray outputs, aov_shaders;
+  AtNode *add(const std::string &name, const std::string &entry) {
+    nodes.emplace_back();
+    AtNode *n = &nodes.back();
+    n->name = name; n->entry.name = entry; n->universe = &uni;
+    uni.nodes.push_back(n);
+    return n;
+  }
+};
+const AtNodeMethods *operator_table() {  // through the plugin's own entry point, as Arnold finds it
+  for (int i = 0; i < 64; ++i) {
+    AtNodeLib lib;
+    memset(&lib, 0, sizeof lib);
+    if (!NodeLoader(i, &lib)) break;
+    if (lib.name && std::string(lib.name) == "lentil_operator" && lib.node_type == AI_NODE_OPERATOR) return lib.methods;
+  }
+  return nullptr;
+}
+std::string dump_aov(const AOVData &a, size_t i) {
+  return "aov " + std::to_string(i) + " name=" + a.name.c_str() + " type=" + std::to_string(a.type) + " original_filter=" + a.original_filter.c_str() +
+         " duplicate=" + std::to_string((int)a.is_duplicate) + " crypto=" + std::to_string((int)a.is_crypto) + " index=" + std::to_string(a.index) +
+         " tokens=[" + a.to.camera_tok + "|" + a.to.aov_name_tok + "|" + a.to.aov_type_tok + "|" + a.to.filter_tok + "|" + a.to.driver_tok + "|" +
+         (a.to.half_flag ? "HALF" : "") + "] driver=" + (a.to.get_driver() ? AiNodeGetName(a.to.get_driver()) : "-") + " output=\"" + a.to.rebuild_output() + "\"\n";
+}
+}  // namespace
+
+// Runs operator_init + operator_cook (`cooks` times, as a re-cooked scene does) on a scene given as text, one item per line:
+//   node <name> <entry>        a node of the scene (filters, drivers, ...)
+//   camera <entry>             node entry of the active camera (default lentil_camera)
+//   aov_shader <name>          a declared node already listed in options.aov_shaders
+//   output <output string>     one element of options.outputs
+// and dumps what is left: cook's return values, OperatorData.aovs, the nodes of the universe with their string parameters and
+// links, options.aov_shaders, and the output list + AOV registrations after the camera's sanitize / rebuild step
+// (aov_data.h:166-189, lentil.h:1046-1058).
+int ref_operator_cook(const char *scene_text, int cooks, char *dump, size_t cap) {
+  const AtNodeMethods *mt = operator_table();
+  if (!mt || !mt->OperatorInit || !mt->OperatorCook || !mt->OperatorCleanup) return LB_ERR_STATE;
+  ShimScene sc;
+  sc.options = sc.add("options", "options");
+  std::string camera_entry = "lentil_camera";
+  std::vector<std::pair<std::string, std::string>> decl;
+  std::vector<std::string> outs, shader_names;
+  {
+    std::string text(scene_text ? scene_text : ""), line;
+    size_t at = 0;
+    while (at <= text.size()) {
+      const size_t nl = text.find('\n', at);
+      line = text.substr(at, nl == std::string::npos ? std::string::npos : nl - at);
+      at = nl == std::string::npos ? text.size() + 1 : nl + 1;
+      if (line.rfind("node ", 0) == 0) {
+        const size_t sp = line.find(' ', 5);
+        if (sp == std::string::npos) return LB_ERR_INVALID;
+        decl.push_back({line.substr(5, sp - 5), line.substr(sp + 1)});
+      } else if (line.rfind("camera ", 0) == 0) camera_entry = line.substr(7);
+      else if (line.rfind("aov_shader ", 0) == 0) shader_names.push_back(line.substr(11));
+      else if (line.rfind("output ", 0) == 0) outs.push_back(line.substr(7));
+      else if (!line.empty()) return LB_ERR_INVALID;
+    }
+  }
+  sc.camera = sc.add("scene_camera", camera_entry);
+  for (auto &d : decl) sc.add(d.first, d.second);
+  sc.op = sc.add("lentil_operator", "lentil_operator");
+  sc.uni.options = sc.options;
+  sc.uni.camera = sc.camera;
+  shim_default_universe() = &sc.uni;
+  sc.outputs.strs = outs;
+  for (auto &nm : shader_names) sc.aov_shaders.ptrs.push_back(AiNodeLookUpByName(&sc.uni, AtString(nm.c_str())));
+  AiNodeSetArray(sc.options, AtString("outputs"), &sc.outputs);
+  AiNodeSetArray(sc.options, AtString("aov_shaders"), &sc.aov_shaders);
+
+  std::string out;
+  void *user = nullptr;
+  out += std::string("init=") + (mt->OperatorInit(sc.op, &user) ? "1" : "0") + "\n";
+  for (int k = 0; k < cooks; ++k) out += "cook" + std::to_string(k) + "=" + (mt->OperatorCook(sc.op, sc.op, user, nullptr, nullptr) ? "1" : "0") + "\n";
+  if (mt->OperatorPostCook) out += std::string("post_cook=") + (mt->OperatorPostCook(sc.op, user) ? "1" : "0") + "\n";
+  OperatorData *od = (OperatorData *)AiNodeGetLocalData(sc.op);
+  for (size_t i = 0; i < od->aovs.size(); ++i) out += dump_aov(od->aovs[i], i);
+  for (AtNode *n : sc.uni.nodes) {
+    out += "node " + n->name + " entry=" + n->entry.name;
+    for (auto &kv : n->params) if (!kv.second.s.empty()) out += " " + kv.first + "=" + kv.second.s;
+    for (auto &kv : n->links) out += " " + kv.first + "<-" + kv.second->name;
+    out += "\n";
+  }
+  AtArray *sh = AiNodeGetArray(sc.options, AtString("aov_shaders"));
+  out += "aov_shaders";
+  for (uint32_t i = 0; i < AiArrayGetNumElements(sh); ++i) out += std::string(" ") + (AiArrayGetPtr(sh, i) ? AiNodeGetName((AtNode *)AiArrayGetPtr(sh, i)) : "null");
+  out += "\n";
+  // what the camera makes of the list (setup_lentil_aovs + rebuild + sanitize, lentil.h:1008-1011,1046-1058)
+  std::vector<AOVData> list(od->aovs.begin(), od->aovs.end());
+  rebuild_arnold_outputs_from_list(&sc.uni, list);
+  AtArray *final_outputs = AiNodeGetArray(sc.options, AtString("outputs"));
+  for (uint32_t i = 0; i < AiArrayGetNumElements(final_outputs); ++i) out += std::string("final_output ") + AiArrayGetStr(final_outputs, i).c_str() + "\n";
+  for (auto &nm : sc.uni.registered_aovs) out += "registered " + nm + "\n";
+  sanitize_aov_list(list);
+  for (size_t i = 0; i < list.size(); ++i) out += "framebuffer " + std::to_string(i) + " " + list[i].name.c_str() + " " + list[i].original_filter.c_str() + "\n";
+  if (final_outputs != &sc.outputs) delete final_outputs;
+  mt->OperatorCleanup(sc.op, user);
+  shim_default_universe() = nullptr;
+  if (dump && cap) { strncpy(dump, out.c_str(), cap - 1); dump[cap - 1] = 0; }
+  return (int)out.size() < (int)cap ? LB_OK : LB_ERR_INVALID;
 }
 
 #ifdef LB_ADAPTOR

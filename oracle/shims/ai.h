@@ -1,6 +1,6 @@
 // ai.h — minimal stand-in for the Arnold SDK header, ONLY to compile the reference's own sources
-// (/root/reference/src/*.h, lentil_camera.cpp, lentil_filter.cpp, lentil_imager.cpp) into oracle/_ref
-// without Arnold.  TEST INFRASTRUCTURE: nothing here is linked into the product.
+// (/root/reference/src/*.h, lentil_camera.cpp, lentil_filter.cpp, lentil_imager.cpp, lentil_operator.cpp,
+// lentil_loader.cpp) into oracle/_ref without Arnold.  TEST INFRASTRUCTURE: nothing here is linked into the product.
 //
 // It models just what those files touch: POD math types with the operators used,
 // a node/universe store with typed parameters, the AOV sample iterator over caller-supplied sample
@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <map>
 #include <set>
 #include <string>
@@ -32,7 +33,8 @@
 enum { AI_TYPE_BYTE = 0, AI_TYPE_INT, AI_TYPE_UINT, AI_TYPE_BOOLEAN, AI_TYPE_FLOAT, AI_TYPE_RGB, AI_TYPE_RGBA, AI_TYPE_VECTOR,
        AI_TYPE_VECTOR2 = 9, AI_TYPE_STRING, AI_TYPE_POINTER, AI_TYPE_NODE, AI_TYPE_ARRAY, AI_TYPE_MATRIX, AI_TYPE_ENUM,
        AI_TYPE_UNDEFINED = 255, AI_TYPE_NONE = 255 };
-enum { AI_NODE_UNDEFINED = 0, AI_NODE_OPTIONS = 1, AI_NODE_CAMERA = 2, AI_NODE_FILTER = 0x40, AI_NODE_DRIVER = 0x80, AI_NODE_ALL = 0xFFFF };
+enum { AI_NODE_UNDEFINED = 0, AI_NODE_OPTIONS = 1, AI_NODE_CAMERA = 2, AI_NODE_FILTER = 0x40, AI_NODE_DRIVER = 0x80,
+       AI_NODE_OPERATOR = 0x1000 /* [EXTERNAL] */, AI_NODE_ALL = 0xFFFF };
 enum { AI_RAY_UNDEFINED = 0, AI_RAY_SHADOW = 2 };
 enum { AI_AOV_BLEND_NONE = 0 };
 
@@ -183,6 +185,7 @@ struct AtNode {
   void *local_data = nullptr;
   AtUniverse *universe = nullptr;
   AtMatrix world_to_camera;  // camera nodes: what AiWorldToCameraMatrix returns (identity unless the harness sets it)
+  std::map<std::string, AtNode *> links;  // AiNodeLink: input name -> the node feeding it
 };
 struct AtRenderSession { int dummy; };
 struct AtUniverse {
@@ -190,6 +193,8 @@ struct AtUniverse {
   std::vector<AtNode *> nodes;
   std::map<std::string, int> entry_counts;  // AiNodeEntryLookUp/AiNodeEntryGetCount
   AtRenderSession session;
+  std::deque<AtNode> created;  // nodes made by AiNode() (lentil_operator.cpp:37,131-132,147-148): owned here, listed in `nodes`
+  std::vector<std::string> registered_aovs;  // AiAOVRegister calls, in order
 };
 inline AtUniverse *&shim_default_universe() { static AtUniverse *u = nullptr; return u; }
 inline const AtParamValueShim &shim_param_get(const AtNode *n, const AtString &k) {
@@ -207,7 +212,7 @@ inline void *AiNodeGetLocalData(const AtNode *n) { return n->local_data; }
 inline void AiNodeSetLocalData(AtNode *n, void *p) { n->local_data = p; }
 inline AtUniverse *AiNodeGetUniverse(const AtNode *n) { return n->universe; }
 inline const char *AiNodeGetName(const AtNode *n) { return n->name.c_str(); }
-inline const AtNodeEntry *AiNodeGetNodeEntry(const AtNode *n) { return &n->entry; }
+inline const AtNodeEntry *AiNodeGetNodeEntry(const AtNode *n) { static const AtNodeEntry none; return n ? &n->entry : &none; }  // [EXTERNAL] a null node has no entry; the stand-in gives it an unnamed one
 inline AtString AiNodeEntryGetNameAtString(const AtNodeEntry *e) { return AtString(e->name.c_str()); }
 inline bool AiNodeIs(const AtNode *n, const AtString &s) { return n->entry.name == s.c_str(); }
 inline AtNode *AiUniverseGetOptions(const AtUniverse *u) { return u->options; }
@@ -237,7 +242,20 @@ inline void *AiArrayGetPtr(const AtArray *a, uint32_t i) { return a->ptrs[i]; }
 inline AtString AiArrayGetStr(const AtArray *a, uint32_t i) { return AtString(a->strs[i].c_str()); }
 inline AtArray *AiArrayAllocate(uint32_t n, uint8_t, uint8_t) { AtArray *a = new AtArray(); a->strs.resize(n); return a; }
 inline void AiArraySetStr(AtArray *a, uint32_t i, const char *s) { a->strs[i] = s; }
-inline bool AiAOVRegister(const char *, uint8_t, int) { return true; }
+// pointer arrays (options.aov_shaders) grow through resize + set (lentil_operator.cpp:139-142,155-158); string arrays keep `strs`
+inline void AiArrayResize(AtArray *a, uint32_t n, uint8_t) { if (!a->strs.empty()) a->strs.resize(n); else a->ptrs.resize(n, nullptr); }
+inline void AiArraySetPtr(AtArray *a, uint32_t i, void *p) { if (i >= a->ptrs.size()) a->ptrs.resize(i + 1, nullptr); a->ptrs[i] = p; }
+inline bool AiAOVRegister(const char *name, uint8_t, int) { if (AtUniverse *u = shim_default_universe()) u->registered_aovs.push_back(name); return true; }
+// scene editing: a node of entry `type` called `name`, owned by the universe
+inline AtNode *AiNode(AtUniverse *u, const AtString &type, const AtString &name = AtString(""), const AtNode * = nullptr) {
+  u->created.emplace_back();
+  AtNode *n = &u->created.back();
+  n->name = name.c_str(); n->entry.name = type.c_str(); n->universe = u;
+  u->nodes.push_back(n);
+  return n;
+}
+inline void AiNodeSetStr(AtNode *n, const AtString &k, const AtString &v) { n->params[k.c_str()].s = v.c_str(); }
+inline bool AiNodeLink(AtNode *src, const AtString &input, AtNode *target) { target->links[input.c_str()] = src; return true; }
 inline const char *AiParamGetTypeName(uint8_t) { return "type"; }
 inline float AiCameraGetShutterStart() { return 0.f; }
 inline float AiCameraGetShutterEnd() { return 0.f; }
@@ -377,6 +395,11 @@ struct AtNodeMethods {
   uint8_t (*FilterOutputType)(const AtNode *, uint8_t);
   void (*FilterPixel)(AtNode *, AtAOVSampleIterator *, void *, uint8_t);
   void (*DriverProcessBucket)(AtNode *, AtOutputIterator *, AtAOVSampleIterator *, int, int, int, int, uint16_t);
+  // operator nodes ([EXTERNAL] ai_operator.h of Arnold 7: init / cleanup / cook / post_cook)
+  bool (*OperatorInit)(AtNode *, void **);
+  bool (*OperatorCleanup)(AtNode *, void *);
+  bool (*OperatorCook)(AtNode *, AtNode *, void *, const AtArray *, struct AtCookContext *);
+  bool (*OperatorPostCook)(AtNode *, void *);
 };
 struct AtNodeLib { const AtNodeMethods *methods; const char *name; int node_type; uint8_t output_type; char version[64]; };
 
@@ -436,6 +459,24 @@ struct AtNodeLib { const AtNodeMethods *methods; const char *name; int node_type
   static AtNodeMethods shim_mtds = {Parameters, Initialize, Update, Finish, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,          \
                                     DriverProcessBucket};                                                                                  \
   const AtNodeMethods *tag = (shim_unused_driver[0] ? &shim_mtds : &shim_mtds)
+
+// operator nodes: the reference's operator only touches `op` (lentil_operator.cpp:19-181); [EXTERNAL] signatures of Arnold 7
+struct AtCookContext { int dummy; };
+#define operator_init static bool OperatorInit(AtNode *op, void **user_data)
+#define operator_cleanup static bool OperatorCleanup(AtNode *op, void *user_data)
+#define operator_cook static bool OperatorCook(AtNode *node, AtNode *op, void *user_data, const AtArray *matching_params, AtCookContext *cook_context)
+#define operator_post_cook static bool OperatorPostCook(AtNode *op, void *user_data)
+#define AI_OPERATOR_NODE_EXPORT_METHODS(tag)                                                                                      \
+  node_parameters;                                                                                                                \
+  operator_init;                                                                                                                  \
+  operator_cleanup;                                                                                                               \
+  operator_cook;                                                                                                                  \
+  operator_post_cook;                                                                                                             \
+  static AtNodeMethods shim_mtds = {Parameters, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, \
+                                    nullptr,    OperatorInit, OperatorCleanup, OperatorCook, OperatorPostCook};                   \
+  const AtNodeMethods *tag = &shim_mtds
+// the plugin's entry point: Arnold calls it with i = 0, 1, ... until it returns false (lentil_loader.cpp:20-28)
+#define node_loader extern "C" AI_EXPORT_LIB bool NodeLoader(int i, AtNodeLib *node)
 
 // parameter declaration macros: the real ones end in a semicolon (the reference omits it twice, lentil_camera.cpp:48-49)
 template <class T> inline void shim_param_decl(AtList *, const T &) {}

@@ -1,4 +1,5 @@
-"""The drop-in claim as a test result: the reference's three Arnold nodes (camera, filter, imager) re-implemented over
+"""The drop-in claim as a test result: the reference's Arnold nodes (camera, filter, imager; operator + loader in test_operator.py and
+the last test here) re-implemented over
 liblentil_b200.so (adaptor/lentil_b200_*.cpp, built against the stand-in SDK headers of oracle/shims/) are driven by the SAME
 harness entry points (oracle/ref_harness.cpp: AtNodeMethods tables, per-sample CreateRay, per-pixel FilterPixel over an
 AtAOVSampleIterator, per-bucket DriverProcessBucket over an AtOutputIterator) as the compiled reference
@@ -144,3 +145,30 @@ def test_cryptomatte_through_the_nodes(ref):
         np.testing.assert_allclose(ta, tr, rtol=2e-4, atol=1e-6)
         want, got = r.resolve(i, fill=-3.0), a.resolve(i, fill=-3.0)
         assert ((want[..., 0] == got[..., 0]) & (np.abs(want[..., 1] - got[..., 1]) < 1e-4)).mean() > 0.999
+
+
+def test_operator_driven_frame_through_the_nodes(ref):
+    """The whole plugin chain on both sides: NodeLoader -> lentil_operator cooks the scene's outputs (every AOV on its original
+    gaussian / closest filter node) -> the camera copies the operator's list (user AOVs + lentil_debug, lentil_time,
+    lentil_raydir) -> filter_pixel -> driver_process_bucket.  Reference: lentil_operator.cpp:25-171, lentil.h:988-1117."""
+    p = po_params(fstop=1.4, focus_dist=35.0, bidir_sample_mult=6)
+    aovs = [("RGBA", 0, 1), ("light0", 0, 0), ("N", 1, 0)]
+    W, H, spp = 96, 54, 9
+    r, a = ref.RefCamera(p), ref.AdaptorCamera(p)
+    fr = workloads.highlight_frame(W, H, spp, r.state.tan_fov, "cpu", n_extra_aov=1)
+    vals = [None, fr["aov_values"][0].numpy(), None]
+    args = (fr["px"].numpy(), fr["py"].numpy(), fr["rgba"].numpy(), fr["pos_cs"].numpy(), 1.0 / spp)
+    for cam, threads in ((r, 1), (a, 4)):
+        cam.use_operator(True)
+        cam.filter_begin(W, H, aovs, spp=spp)
+        cam.filter_accumulate(*args, aov_values=vals, nthreads=threads)
+    for i in (0, 1):  # gaussian AOVs
+        want, got = r.resolve(i), a.resolve(i)
+        assert rel_l1(got, want) <= 3e-3 and psnr(got, want) >= 50.0, (aovs[i][0], rel_l1(got, want), psnr(got, want))
+    for i in (2, 3):  # closest: the user's N, and lentil_debug (made by the operator; samples * redistribute of the nearest sample)
+        want, got = r.resolve(i), a.resolve(i)
+        assert (np.abs(got - want).max(axis=2) > 1e-6).mean() <= 5e-3, i
+    assert np.abs(r.resolve(3)).max() > 0  # lentil_debug is live
+    for i in (4, 5):  # lentil_time (zero in this scene), lentil_raydir: gaussian helper outputs
+        want, got = r.resolve(i), a.resolve(i)
+        assert rel_l1(got, want) <= 3e-3 or np.abs(want).max() == 0 and np.abs(got).max() == 0, i
