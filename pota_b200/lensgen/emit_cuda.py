@@ -265,7 +265,7 @@ def lens_unit(lens) -> tuple[str, dict]:
             "__global__ void __launch_bounds__(128%s)" % K2F_MIN_BLOCKS,
             "k_filter_splat_%d%s, const __grid_constant__ FoldB%d C) {" % (k, k2_sig, k),
             "  splat_persistent(EvalFB%d{C}, cam, fc, aovs, s, work, counters, sample_base);" % k, "}", "",
-            "__global__ void __launch_bounds__(128%s)" % K2W_MIN_BLOCKS,
+            "__global__ void __launch_bounds__(128%s)" % K2F_MIN_BLOCKS,
             "k_filter_splat_w550_%d%s) {" % (k, k2_sig),
             "  splat_persistent(EvalIB%d{}, cam, fc, aovs, s, work, counters, sample_base);" % k, "}", "",
             "__global__ void __launch_bounds__(128%s)" % K2_MIN_BLOCKS,
@@ -307,7 +307,6 @@ K1_MIN_BLOCKS = ", " + os.environ.get("LB_K1_MINBLOCKS", "4")
 K2_MIN_BLOCKS = ", " + os.environ.get("LB_K2_MINBLOCKS", "5")
 K1F_MIN_BLOCKS = ", " + os.environ.get("LB_K1F_MINBLOCKS", "4")
 K2F_MIN_BLOCKS = ", " + os.environ.get("LB_K2F_MINBLOCKS", "5")
-K2W_MIN_BLOCKS = ", " + os.environ.get("LB_K2W_MINBLOCKS", os.environ.get("LB_K2F_MINBLOCKS", "5"))  # the 550 nm immediates kernel
 
 
 def emit_cuda(out_dir: str, only=None):
