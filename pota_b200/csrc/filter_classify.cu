@@ -31,9 +31,17 @@ __device__ float additional_luminance_soft_trans(const FilterConsts &fc, float l
 }
 
 // cryptomatte_construct_cache (lentil.h:779-811) for AOV `a` of sample i: walks the depth sub-samples in order,
-// merging equal ids as the reference's std::map<float,float> does, and leaves the packed {id, weight} list in the
-// batch scratch for the splat kernel.  Float arithmetic operation by operation as there (this unit is -fmad=false).
-__device__ void crypto_build_cache(const AovSet &aovs, const SampleIO &s, int a, size_t i) {
+// merging equal ids as the reference's std::map<float,float> does, into a packed {id, weight} list.  Float arithmetic
+// operation by operation as there (this unit is -fmad=false).
+// A redistributed sample leaves the list in the batch scratch for the splat kernel.  A pass-through sample (`!redistribute`)
+// adds it to its own pixel right here -- add_to_buffer_cryptomatte (lentil.h:814-819) from filter_and_add_to_buffer_new
+// (:938-955), what crypto_add (filter_common.cuh) does for a splat -- and writes nothing: 33 M samples x 3 AOVs x 4 entries would
+// be 3.2 GB of scratch that nothing reads again.
+// (kAddPass = false: every sample writes its list and pass-through samples add it later through crypto_add, the form the kernel
+// for frames WITHOUT cryptomatte AOVs keeps so that it stays the kernel it was.)
+template <bool kAddPass>
+__device__ void crypto_build_cache(const AovSet &aovs, const SampleIO &s, int a, size_t i, bool redistribute, unsigned pixel,
+                                   FilterCounters *counters) {
   const int D = aovs.crypto_depth;
   const int stride = D > 1 ? D : 1;
   float key[kCryptoMaxDepth], wgt[kCryptoMaxDepth];
@@ -58,10 +66,19 @@ __device__ void crypto_build_cache(const AovSet &aovs, const SampleIO &s, int a,
     add(sample_value, sub_sample_weight);
   }
   if ((double)quota > 0.0) add(sample_value, quota);
-  float2 *out = aovs.crypto_cache[a] + i * (size_t)stride;
-  for (int j = 0; j < stride; ++j) out[j] = j < m ? make_float2(key[j], wgt[j]) : make_float2(__uint_as_float(kCryptoFree), 0.0f);
+  if (!kAddPass || redistribute) {
+    float2 *out = aovs.crypto_cache[a] + i * (size_t)stride;
+    for (int j = 0; j < stride; ++j) out[j] = j < m ? make_float2(key[j], wgt[j]) : make_float2(__uint_as_float(kCryptoFree), 0.0f);
+  } else {
+    const float sample_weight = s.inv_density;
+    if (a == aovs.crypto_first) red_add(&aovs.buffer[a][pixel].x, sample_weight);  // crypto_total_weight, one plane for all
+    for (int j = 0; j < m && j < stride; ++j)
+      crypto_insert(aovs.crypto_key[a], aovs.crypto_wgt[a], aovs.crypto_slots, pixel, key[j], wgt[j] * sample_weight, counters);
+  }
 }
 
+// kCryptoFrame: the frame has cryptomatte AOVs (picked by the host).
+template <bool kCryptoFrame>
 __global__ void __launch_bounds__(256)
 k_filter_classify(const __grid_constant__ FilterConsts fc, const __grid_constant__ AovSet aovs, const __grid_constant__ SampleIO s,
                   WorkItem *__restrict__ work, FilterCounters *__restrict__ counters, uint64_t sample_base) {
@@ -122,9 +139,13 @@ k_filter_classify(const __grid_constant__ FilterConsts fc, const __grid_constant
     debug_val = (float)(samples * (redistribute ? 1 : 0));  // lentil_debug value, taken at :209-211
     if (fc.camera_type == 1 && (double)fabsf(csp[2]) < fc.lens_length_tenth) redistribute = false;  // :240, PolynomialOptics case only
     const int px = __ldg(s.px + i), py = __ldg(s.py + i);
-    for (int a = 0; a < fc.n_aov; ++a)  // lentil_filter.cpp:167-169
-      if (aovs.filter[a] == 2) crypto_build_cache(aovs, s, a, i);
+    if (!kCryptoFrame)
+      for (int a = 0; a < fc.n_aov; ++a)  // lentil_filter.cpp:167-169
+        if (aovs.filter[a] == 2) crypto_build_cache<false>(aovs, s, a, i, redistribute, 0u, counters);
     pixel = (unsigned)fc.xres * (unsigned)py + (unsigned)px;
+    if (kCryptoFrame)
+      for (int a = 0; a < fc.n_aov; ++a)
+        if (aovs.filter[a] == 2) crypto_build_cache<true>(aovs, s, a, i, redistribute, pixel, counters);
     if (aovs.debug_samples) aovs.debug_samples[i] = (uint16_t)debug_val;
   }
   const int lane = threadIdx.x & 31;
@@ -141,8 +162,8 @@ k_filter_classify(const __grid_constant__ FilterConsts fc, const __grid_constant
     const unsigned heads = __ballot_sync(0xffffffffu, head);
     const unsigned above = lane < 31 ? heads >> (lane + 1) : 0u;  // head flags of the lanes after this one
     for (int a = 0; a < fc.n_aov; ++a) {
-      if (aovs.filter[a] == 2) {  // cryptomatte tables: per sample
-        if (pass) crypto_add(aovs, a, i, true, pixel, s.inv_density, counters);
+      if (aovs.filter[a] == 2) {  // cryptomatte tables: per sample; kCryptoFrame: already added where the list was built
+        if (!kCryptoFrame && pass) crypto_add(aovs, a, i, true, pixel, s.inv_density, counters);
       } else if (aovs.filter[a] == 1) {  // closest: depth key
         if (pass) {
           const float white[3] = {1.f, 1.f, 1.f};
@@ -200,7 +221,9 @@ k_filter_classify(const __grid_constant__ FilterConsts fc, const __grid_constant
 cudaError_t launch_filter_classify(const FilterConsts &fc, const AovSet &aovs, const SampleIO &s, WorkItem *work,
                                    FilterCounters *counters, uint64_t sample_base, cudaStream_t stream) {
   if (s.n == 0) return cudaSuccess;
-  k_filter_classify<<<(unsigned)((s.n + 255) / 256), 256, 0, stream>>>(fc, aovs, s, work, counters, sample_base);
+  const unsigned grid = (unsigned)((s.n + 255) / 256);
+  if (aovs.crypto_first >= 0) k_filter_classify<true><<<grid, 256, 0, stream>>>(fc, aovs, s, work, counters, sample_base);
+  else k_filter_classify<false><<<grid, 256, 0, stream>>>(fc, aovs, s, work, counters, sample_base);
   return cudaGetLastError();
 }
 

@@ -63,6 +63,23 @@ LB_DEV void add_to_buffer(const AovSet &aovs, int a, unsigned pixel, float4 v, f
 // ---- cryptomatte ----------------------------------------------------------------------------------
 // aov.crypto_hash_map[px][id] += w (lentil.h:817) on a fixed-size open-addressed table: claim a slot with a
 // compare-and-swap on the id bits, then a float reduction on its weight.
+// crypto_insert_at: the same probing from slot h, whose id has already been read as `cur` (crypto_add_hoisted).
+LB_DEV void crypto_insert_at(uint32_t *__restrict__ k0, float *__restrict__ w0, int slots, uint32_t key, float w, unsigned h, uint32_t cur,
+                             FilterCounters *counters) {
+  for (int t = 0; t < slots; ++t) {
+    if (t) cur = *(volatile uint32_t *)(k0 + h);
+    if (cur == kCryptoFree) cur = atomicCAS(k0 + h, kCryptoFree, key);
+    if (cur == kCryptoFree || cur == key) {
+      red_add(w0 + h, w);
+      return;
+    }
+    h = h + 1 == (unsigned)slots ? 0u : h + 1;
+  }
+  atomicAdd(&counters->crypto_dropped, 1ull);
+}
+LB_DEV uint32_t crypto_key_bits(float id) { return __float_as_uint(id == 0.0f ? 0.0f : id); }
+LB_DEV unsigned crypto_home_slot(uint32_t key, int slots) { return ((key * 2654435761u) >> 15) % (unsigned)slots; }
+
 LB_DEV void crypto_insert(uint32_t *__restrict__ keys, float *__restrict__ wgts, int slots, unsigned pixel, float id, float w,
                           FilterCounters *counters) {
   const uint32_t key = __float_as_uint(id == 0.0f ? 0.0f : id);  // -0 and +0 are one std::map key
@@ -82,7 +99,7 @@ LB_DEV void crypto_insert(uint32_t *__restrict__ keys, float *__restrict__ wgts,
 }
 
 // add_to_buffer_cryptomatte (lentil.h:814-819) for AOV `a` and the cached {id, weight} list of source sample i.
-// Called warp-converged from the splat kernels (`on`: this lane has a splat at `pixel`), per thread from classify.
+// Called warp-converged from the splat kernels (`on`: this lane has a splat at `pixel`).
 LB_DEV void crypto_add(const AovSet &aovs, int a, size_t i, bool on, unsigned pixel, float sample_weight, FilterCounters *counters) {
   const int stride = aovs.crypto_depth > 1 ? aovs.crypto_depth : 1;
   const float2 *e = aovs.crypto_cache[a] + i * (size_t)stride;
@@ -94,15 +111,60 @@ LB_DEV void crypto_add(const AovSet &aovs, int a, size_t i, bool on, unsigned pi
   }
 }
 
+// The same for the thin-lens splat kernels, whose attempts cost ~650 instructions: with cryptomatte AOVs they wait on the slot probes
+// (ncu: long_scoreboard is the top stall, issue slots 40 % busy; profiles/r02_crypto_splat_ncu.txt), and
+// one id's probe -> reduction does not depend on another's: the home slots of up to four ids are read back to back, then each id
+// continues from the value read.  Same atomics as one crypto_insert per id; a slot's id never changes once claimed, so a value
+// read early is still right when it matches, and a stale "free" just goes through the compare-and-swap as always.
+LB_DEV void crypto_add_hoisted(const AovSet &aovs, int a, size_t i, bool on, unsigned pixel, float sample_weight, FilterCounters *counters) {
+  const int stride = aovs.crypto_depth > 1 ? aovs.crypto_depth : 1;
+  const float2 *e = aovs.crypto_cache[a] + i * (size_t)stride;
+  if (on && a == aovs.crypto_first) red_add(&aovs.buffer[a][pixel].x, sample_weight);  // crypto_total_weight, one plane for every cryptomatte AOV
+  const int slots = aovs.crypto_slots;
+  const size_t row = on ? (size_t)pixel * slots : 0;  // `pixel` means nothing on a lane without a splat
+  uint32_t *k0 = aovs.crypto_key[a] + row;
+  float *w0 = aovs.crypto_wgt[a] + row;
+  for (int j0 = 0; j0 < stride; j0 += 4) {
+    float2 kv[4];
+    uint32_t key[4], cur[4];
+    unsigned h[4];
+    int n = 0;  // warp-uniform: the list belongs to the source sample
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (j0 + k < stride && n == k) {
+        kv[k] = e[j0 + k];
+        if (__float_as_uint(kv[k].x) != kCryptoFree) n = k + 1;
+      }
+    }
+    if (on) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (k < n) {
+          key[k] = crypto_key_bits(kv[k].x);
+          h[k] = crypto_home_slot(key[k], slots);
+          cur[k] = *(volatile uint32_t *)(k0 + h[k]);
+        }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (k < n) crypto_insert_at(k0, w0, slots, key[k], kv[k].y * sample_weight, h[k], cur[k], counters);
+    }
+    if (n < 4) break;
+  }
+}
+
 // every AOV of one splat (lentil_filter.cpp:295-298 / :442-445).  Warp-converged: the source sample i and with it
 // the AOV values are warp-uniform, the target pixel is per lane (< 0: this lane has nothing to add).
 // skip_aov: an AOV this lane has already accumulated elsewhere (the shared-memory window of the thin-lens tile kernel), or -1.
+// kHoistProbes: crypto_add_hoisted for the cryptomatte AOVs (the thin-lens kernels; the polynomial-optics kernels are bound by their
+// Newton trips and keep the form that costs them no registers).
+template <bool kHoistProbes = false>
 LB_DEV void splat_all_aovs(const FilterConsts &fc, const AovSet &aovs, const SampleIO &s, size_t i, float debug_val, int pixel,
                            float add_energy, float depth, float weight, const float rgb_weight[3], uint64_t sample_global,
                            FilterCounters *counters, int skip_aov = -1) {
   for (int a = 0; a < fc.n_aov; ++a) {
     if (aovs.filter[a] == 2) {
-      crypto_add(aovs, a, i, pixel >= 0, (unsigned)pixel, weight, counters);
+      if (kHoistProbes) crypto_add_hoisted(aovs, a, i, pixel >= 0, (unsigned)pixel, weight, counters);
+      else crypto_add(aovs, a, i, pixel >= 0, (unsigned)pixel, weight, counters);
     } else {
       const float4 v = aov_value(aovs, s, a, i, debug_val);
       if (pixel >= 0 && a != skip_aov) add_to_buffer(aovs, a, (unsigned)pixel, v, add_energy, depth, weight, rgb_weight, sample_global);

@@ -307,7 +307,9 @@ struct TileView {   // the CTA's window; tile4 == nullptr: no tile (every splat 
   int org_x, org_y, aov;  // window origin (region-relative pixels); index of the AOV kept in the window
 };
 
-template <int kTile>
+// kHoistProbes: the instantiation for frames with cryptomatte AOVs (crypto_add_hoisted, filter_common.cuh); frames without them run
+// the other one, which is the kernel as it was
+template <int kTile, bool kHoistProbes = false>
 LB_DEV void thinlens_splat_item(const CamConsts<float> &cam, const ThinConsts &tl, const FilterConsts &fc, const AovSet &aovs, const SampleIO &s,
                                 const WorkItem &w, FilterCounters *counters, uint64_t sample_base, const TileView &tv) {
   const int lane = threadIdx.x & 31;
@@ -352,9 +354,9 @@ LB_DEV void thinlens_splat_item(const CamConsts<float> &cam, const ThinConsts &t
           ++n_tile;
         }
         // lanes inside the window skip that AOV below; the others send it to L2
-        splat_all_aovs(fc, aovs, s, i, (float)samples, pixel, w.add_energy, depth, weight, rgbw, sample_base + i, counters, inside ? tv.aov : -1);
+        splat_all_aovs<kHoistProbes>(fc, aovs, s, i, (float)samples, pixel, w.add_energy, depth, weight, rgbw, sample_base + i, counters, inside ? tv.aov : -1);
       } else {
-        splat_all_aovs(fc, aovs, s, i, (float)samples, pixel, w.add_energy, depth, weight, rgbw, sample_base + i, counters, -1);
+        splat_all_aovs<kHoistProbes>(fc, aovs, s, i, (float)samples, pixel, w.add_energy, depth, weight, rgbw, sample_base + i, counters, -1);
       }
     }
     count += __popc(ok);
@@ -373,6 +375,7 @@ LB_DEV void thinlens_splat_item(const CamConsts<float> &cam, const ThinConsts &t
 // work_heads[4]: 0 = not decided, 1 = direct kernel, 2 = tile kernel (k_thinlens_pick; the other kernel returns at once)
 constexpr unsigned kPickDirect = 1u, kPickTile = 2u;
 
+template <bool kHoistProbes>
 __global__ void __launch_bounds__(128)
 k_filter_splat_thinlens(const __grid_constant__ CamConsts<float> cam, const __grid_constant__ ThinConsts tl, const __grid_constant__ FilterConsts fc,
                         const __grid_constant__ AovSet aovs, const __grid_constant__ SampleIO s, const WorkItem *__restrict__ work,
@@ -387,7 +390,7 @@ k_filter_splat_thinlens(const __grid_constant__ CamConsts<float> cam, const __gr
     idx = __shfl_sync(0xffffffffu, idx, 0);
     if (idx >= n_work) break;
     const WorkItem w = work[idx];
-    thinlens_splat_item<0>(cam, tl, fc, aovs, s, w, counters, sample_base, none);
+    thinlens_splat_item<0, kHoistProbes>(cam, tl, fc, aovs, s, w, counters, sample_base, none);
   }
 }
 
@@ -528,7 +531,10 @@ cudaError_t launch_filter_splat_thinlens(const CamConsts<float> &cam, const Thin
   const bool tile_possible = tile_aov >= 0 && fc.xres >= kTile && fc.yres >= kTile;
   const int force = !tile_possible || mode == 0 ? 1 : (mode == 1 ? 2 : 0);
   if (force != 1) k_thinlens_pick<<<1, 128, 0, stream>>>(tl, fc, aovs, work, kTile, force);  // (work_heads[4] == 0 also means direct)
-  if (force != 2) k_filter_splat_thinlens<<<num_sms * 8, 128, 0, stream>>>(cam, tl, fc, aovs, s, work, counters, sample_base);
+  if (force != 2) {
+    if (aovs.crypto_first >= 0) k_filter_splat_thinlens<true><<<num_sms * 8, 128, 0, stream>>>(cam, tl, fc, aovs, s, work, counters, sample_base);
+    else k_filter_splat_thinlens<false><<<num_sms * 8, 128, 0, stream>>>(cam, tl, fc, aovs, s, work, counters, sample_base);
+  }
   if (force != 1) {
     const cudaError_t attr = cudaFuncSetAttribute(k_filter_splat_thinlens_tile<kTile, kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (attr != cudaSuccess) return attr;
