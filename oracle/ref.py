@@ -43,6 +43,7 @@ def _declare_scenario_api(L):
     L.ref_filter_crypto.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp]
     L.ref_camera_use_operator.argtypes = [vp, C.c_int]
     L.ref_node_loader.argtypes = [C.c_char_p, C.c_size_t]
+    L.ref_node_interface.argtypes = [C.c_char_p, C.c_size_t]
     L.ref_operator_cook.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_size_t]
     return L
 
@@ -51,6 +52,16 @@ def node_loader(L) -> list[str]:
     """what NodeLoader(i, ...) answers for i = 0, 1, ... (lentil_loader.cpp:20-28), one line per node"""
     buf = C.create_string_buffer(1 << 14)
     L.ref_node_loader(buf, len(buf))
+    return buf.value.decode().splitlines()
+
+
+def node_interface(L) -> list[str]:
+    """what every node of the library declares to the renderer: parameters (type, name, default, enum strings), metadata, the
+    filter's required AOVs / width / output types, the imager's render hints (ref_node_interface in oracle/ref_harness.cpp)"""
+    buf = C.create_string_buffer(1 << 16)
+    rc = L.ref_node_interface(buf, len(buf))
+    if rc != 0:
+        raise RuntimeError(f"ref_node_interface: {rc}")
     return buf.value.decode().splitlines()
 
 

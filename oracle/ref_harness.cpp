@@ -399,6 +399,53 @@ int ref_node_loader(char *dump, size_t cap) {
   return i;
 }
 
+// What each node of the plugin declares to the renderer, as text: parameter declarations (type, name, default, enum strings) and
+// metadata from node_parameters; for the filter node the AOVs node_initialize requires, the width node_update sets and
+// filter_output_type over the data types; for the imager the render hints node_update sets.
+int ref_node_interface(char *dump, size_t cap) {
+  std::string out;
+  for (int i = 0; i < 64; ++i) {
+    AtNodeLib lib;
+    memset(&lib, 0, sizeof lib);
+    if (!NodeLoader(i, &lib)) break;
+    out += std::string("node ") + lib.name + "\n";
+    AtList list;
+    AtNodeEntry entry;
+    entry.name = lib.name;
+    if (lib.methods->Parameters) lib.methods->Parameters(&list, &entry);
+    for (auto &d : list.decls) out += "  param " + d + "\n";
+    for (auto &m : entry.meta) out += "  meta " + m + "\n";
+    AtUniverse uni;
+    AtNode options, node;
+    options.name = "options"; options.entry.name = "options";
+    node.name = lib.name; node.entry.name = lib.name;
+    uni.options = &options; uni.nodes = {&options, &node};
+    options.universe = node.universe = &uni;
+    shim_default_universe() = &uni;
+    if (lib.node_type == AI_NODE_FILTER) {
+      lib.methods->Initialize(&uni.session, &node);
+      for (auto &a : node.required_aovs) out += "  requires " + a + "\n";
+      for (int oidn = 0; oidn < 2; ++oidn) {  // an OIDN denoiser imager in the scene narrows the filter (lentil_filter.cpp:33-38)
+        uni.entry_counts["imager_denoiser_oidn"] = oidn;
+        lib.methods->Update(&uni.session, &node);
+        out += "  filter_width oidn=" + std::to_string(oidn) + " " + shim_flt(node.filter_width) + "\n";
+      }
+      for (int t : {AI_TYPE_BYTE, AI_TYPE_INT, AI_TYPE_UINT, AI_TYPE_BOOLEAN, AI_TYPE_FLOAT, AI_TYPE_RGB, AI_TYPE_RGBA, AI_TYPE_VECTOR, AI_TYPE_VECTOR2,
+                    AI_TYPE_STRING, AI_TYPE_POINTER, AI_TYPE_NODE, AI_TYPE_ARRAY, AI_TYPE_MATRIX})
+        out += "  output_type " + std::to_string(t) + " -> " + std::to_string((int)lib.methods->FilterOutputType(&node, (uint8_t)t)) + "\n";
+      lib.methods->Finish(&node);
+    } else if (lib.node_type == AI_NODE_DRIVER) {
+      lib.methods->Initialize(&uni.session, &node);
+      lib.methods->Update(&uni.session, &node);
+      for (auto &h : uni.session.hints) out += "  hint " + h + "\n";
+      lib.methods->Finish(&node);
+    }
+    shim_default_universe() = nullptr;
+  }
+  if (dump && cap) { strncpy(dump, out.c_str(), cap - 1); dump[cap - 1] = 0; }
+  return out.size() < cap ? LB_OK : LB_ERR_INVALID;
+}
+
 namespace {
 struct ShimScene {  // a universe described line by line (ref_operator_cook)
   AtUniverse uni;

@@ -177,7 +177,7 @@ struct AtNode;
 struct AtUniverse;
 struct AtArray { std::vector<std::string> strs; std::vector<void *> ptrs; };
 struct AtParamValueShim { int i = 0; float f = 0; bool b = false; std::string s; void *p = nullptr; AtArray *a = nullptr; };
-struct AtNodeEntry { std::string name; int count = 0; };
+struct AtNodeEntry { std::string name; int count = 0; std::vector<std::string> meta; /* AiMetaDataSet* calls, in order */ };
 struct AtNode {
   std::string name;
   AtNodeEntry entry;
@@ -186,8 +186,10 @@ struct AtNode {
   AtUniverse *universe = nullptr;
   AtMatrix world_to_camera;  // camera nodes: what AiWorldToCameraMatrix returns (identity unless the harness sets it)
   std::map<std::string, AtNode *> links;  // AiNodeLink: input name -> the node feeding it
+  std::vector<std::string> required_aovs;  // AiFilterInitialize: the AOVs a filter node asks the renderer for
+  float filter_width = 0.f;                // AiFilterUpdate
 };
-struct AtRenderSession { int dummy; };
+struct AtRenderSession { int dummy; std::vector<std::string> hints; /* AiRenderSetHintInt calls */ };
 struct AtUniverse {
   AtNode *options = nullptr, *camera = nullptr;
   std::vector<AtNode *> nodes;
@@ -218,7 +220,7 @@ inline bool AiNodeIs(const AtNode *n, const AtString &s) { return n->entry.name 
 inline AtNode *AiUniverseGetOptions(const AtUniverse *u) { return u->options; }
 inline AtNode *AiUniverseGetCamera(const AtUniverse *u) { return u->camera; }
 inline AtRenderSession *AiUniverseGetRenderSession(AtUniverse *u) { return &u->session; }
-inline void AiRenderSetHintInt(AtRenderSession *, const AtString &, int) {}
+inline void AiRenderSetHintInt(AtRenderSession *rs, const AtString &k, int v) { if (rs) rs->hints.push_back(std::string(k.c_str()) + "=" + std::to_string(v)); }
 inline AtNode *AiNodeLookUpByName(const AtUniverse *u, const AtString &name) {
   for (AtNode *n : u->nodes) if (n->name == name.c_str()) return n;
   return nullptr;
@@ -263,11 +265,18 @@ inline void AiCameraInitialize(AtNode *) {}
 inline void AiCameraUpdate(AtNode *, bool) {}
 inline void AiCameraToWorldMatrix(const AtNode *, float, AtMatrix &m) { m = AtMatrix(); }
 inline void AiWorldToCameraMatrix(const AtNode *n, float, AtMatrix &m) { m = n ? n->world_to_camera : AtMatrix(); }
-inline void AiFilterInitialize(AtNode *, bool, const char **) {}
-inline void AiFilterUpdate(AtNode *, float) {}
+inline void AiFilterInitialize(AtNode *n, bool, const char **required) {
+  n->required_aovs.clear();
+  for (; required && *required; ++required) n->required_aovs.push_back(*required);
+}
+inline void AiFilterUpdate(AtNode *n, float width) { n->filter_width = width; }
 inline void AiDriverInitialize(AtNode *, bool) {}
-inline void AiMetaDataSetBool(AtNodeEntry *, const char *, const char *, bool) {}
-inline void AiMetaDataSetStr(AtNodeEntry *, const char *, const AtString &, const AtString &) {}
+inline void AiMetaDataSetBool(AtNodeEntry *e, const char *param, const char *name, bool v) {
+  if (e) e->meta.push_back(std::string(param ? param : "") + ":" + name + "=" + (v ? "true" : "false"));
+}
+inline void AiMetaDataSetStr(AtNodeEntry *e, const char *param, const AtString &name, const AtString &v) {
+  if (e) e->meta.push_back(std::string(param ? param : "") + ":" + name.c_str() + "=" + v.c_str());
+}
 
 // ---- scene rays: there is no scene, nothing is ever occluded ---------------------------------------------
 struct AtShaderGlobals { int dummy; };
@@ -382,7 +391,7 @@ inline bool AiOutputIteratorGetNext(AtOutputIterator *it, AtString *name, int *t
 // ---- camera I/O, node method tables and the node-definition macros ------------------------------------------------
 struct AtCameraInput { float sx, sy, dsx, dsy, lensx, lensy, relative_time; };
 struct AtCameraOutput { AtVector origin, dir, dOdx, dOdy, dDdx, dDdy; AtRGB weight; };
-struct AtList { int dummy; };
+struct AtList { int dummy; std::vector<std::string> decls; /* AiParameter* declarations, in order */ };
 struct AtNodeMethods {
   void (*Parameters)(AtList *, AtNodeEntry *);
   void (*Initialize)(AtRenderSession *, AtNode *);
@@ -479,9 +488,12 @@ struct AtCookContext { int dummy; };
 #define node_loader extern "C" AI_EXPORT_LIB bool NodeLoader(int i, AtNodeLib *node)
 
 // parameter declaration macros: the real ones end in a semicolon (the reference omits it twice, lentil_camera.cpp:48-49)
-template <class T> inline void shim_param_decl(AtList *, const T &) {}
-#define AiParameterEnum(n, d, e) shim_param_decl(params, n);
-#define AiParameterInt(n, d) shim_param_decl(params, n);
-#define AiParameterFlt(n, d) shim_param_decl(params, n);
-#define AiParameterBool(n, d) shim_param_decl(params, n);
-#define AiParameterStr(n, d) shim_param_decl(params, n);
+inline std::string shim_text(const char *c) { return c ? c : ""; }
+inline std::string shim_text(const AtString &a) { return a.c_str(); }
+inline std::string shim_enum_values(const char **e) { std::string v; for (; e && *e; ++e) v += (v.empty() ? "" : ",") + std::string(*e); return v; }
+inline std::string shim_flt(double d) { char b[64]; snprintf(b, sizeof b, "%.9g", d); return b; }
+#define AiParameterEnum(n, d, e) params->decls.push_back("enum " + shim_text(n) + " default=" + std::to_string((int)(d)) + " values=" + shim_enum_values(e));
+#define AiParameterInt(n, d) params->decls.push_back("int " + shim_text(n) + " default=" + std::to_string((int)(d)));
+#define AiParameterFlt(n, d) params->decls.push_back("flt " + shim_text(n) + " default=" + shim_flt((float)(d)));
+#define AiParameterBool(n, d) params->decls.push_back("bool " + shim_text(n) + " default=" + ((d) ? "true" : "false"));
+#define AiParameterStr(n, d) params->decls.push_back("str " + shim_text(n) + " default=\"" + shim_text(d) + "\"");

@@ -96,7 +96,7 @@ def main():
         if "camera lentil_camera" not in lines:
             scenes[key + "+lentil_camera"] = "\n".join("camera lentil_camera" if ln.startswith("camera ") else ln for ln in lines)
     scenes.update(HAND)
-    out = {"loader": ref.node_loader(L), "scenes": {}}
+    out = {"loader": ref.node_loader(L), "interface": ref.node_interface(L), "scenes": {}}
     for name, scene in scenes.items():
         out["scenes"][name] = {"scene": scene, "cook1": ref.operator_cook(L, scene, 1), "cook2": ref.operator_cook(L, scene, 2)}
     with open(os.path.join(HERE, "operator_scenes.json"), "w") as f:

@@ -5,7 +5,8 @@
 Both libraries run the same scenario code (oracle/ref_harness.cpp: ref_operator_cook, ref_node_loader) on the `options.outputs`
 lists and filter / driver nodes of the reference's own test scenes (/root/reference/tests/*/*.ass, extracted by
 tests/golden/make_operator_scenes.py into tests/golden/operator_scenes.json together with the reference's answers) and on
-hand-written scenes covering every branch of lentil_operator.cpp:44-99.  Compared: cook's return value, every field of every
+hand-written scenes covering every branch of lentil_operator.cpp:44-99, and dump what every node DECLARES to the renderer
+(ref_node_interface: parameters, metadata, required AOVs, filter width / output types, render hints).  Compared: cook's return value, every field of every
 OperatorData entry (name, type, remembered filter kind, duplicate flag, the five output tokens + HALF, resolved driver), the
 nodes and links the cook creates, options.aov_shaders, and what the camera's rebuild + sanitize step turns the list into (the
 framebuffers lb_filter_begin is asked for).  Host-side string work: exact equality.  No GPU needed."""
@@ -54,8 +55,21 @@ def test_node_loader_matches_reference(adaptor):
     assert [ln.split()[-1] for ln in got] == ["methods=camera", "methods=filter", "methods=imager", "methods=operator"]
 
 
+def test_node_interface_matches_reference(adaptor):
+    """what the four nodes declare to the renderer -- the 29 camera parameters with their types, defaults and enum strings
+    (lentil_camera.cpp:19-52: a scene file written for the reference must load on the adaptor's node), node metadata, the AOVs the
+    filter node requires (lentil_filter.cpp:16-25), its width with and without an OIDN imager (:33-38), filter_output_type over
+    the data types (:45-63), the imager's `enable` parameter, subtype and render hints (lentil_imager.cpp:19-38)"""
+    got = ref.node_interface(adaptor)
+    assert got == FIX["interface"]
+    cam = got[got.index("node lentil_camera") + 1:got.index("node lentil_filter")]
+    assert len([ln for ln in cam if ln.startswith("  param ")]) == 29
+    assert "  param enum lens_model default=16 values=" in "\n".join(cam) and "  requires FLOAT lentil_bidir_ignore" in got
+
+
 def test_golden_is_the_compiled_reference(reference):
     assert ref.node_loader(reference) == FIX["loader"]
+    assert ref.node_interface(reference) == FIX["interface"]
     for name in SCENES:
         sc = FIX["scenes"][name]
         assert ref.operator_cook(reference, sc["scene"], 1) == sc["cook1"], name
